@@ -1,0 +1,20 @@
+// Internal interface of the ICP tracker; implemented in icp_kernels.cu.
+#pragma once
+#include "common.cuh"
+#include "se3.h"
+
+namespace icp
+{
+struct Tracker;
+
+// kind: 1 = extended (ITMExtendedTracker, the reference's compiled-in default), 2 = icp (ITMDepthTracker)
+Tracker *create_tracker(int kind, int W, int H, float vfmin, float vfmax);
+void destroy_tracker(Tracker *t);
+
+// B1 stand-alone: short mm -> float m (ITMViewBuilder_Shared.h:27-36)
+void convert_depth(const short *depth_mm, float *depth_f, int W, int H, cudaStream_t st);
+
+// TrackCamera: updates *pose_d in place (host pose, final value read back once per frame)
+int track_camera(Tracker *t, const float *depth_f, const float4 *pointsMap, const float4 *normalsMap, float fx, float fy, float cx, float cy,
+                 const Mat4 &scenePose, int trackingFrames, se3::Pose *pose_d, cudaStream_t st);
+} // namespace icp

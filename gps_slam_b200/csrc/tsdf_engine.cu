@@ -1,0 +1,360 @@
+// TSDF engine object + its C ABI (include/gpsslam_b200.h, section B).
+// Host logic mirrors ITMBasicEngine::ProcessFrame / runRaycast (reference InfiniTAM/ITMLib/Core/ITMBasicEngine.tpp:260-385,
+// 500-526) and ITMTrackingController::Prepare (Core/ITMTrackingController.h:66-102): same stage order, same pose handling
+// (SetInvM + Coerce through se3::Pose), but every stage is an asynchronous launch on one stream with no host round trip.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gpsslam_b200.h"
+#include "common.cuh"
+#include "icp.h"
+#include "se3.h"
+#include "tsdf.h"
+
+static thread_local std::string g_err;
+int gs_set_error(const char *file, int line, const char *msg)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s:%d: %s", file, line, msg);
+    g_err = buf;
+    return 1;
+}
+extern "C" const char *gsb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *gsb_version(void) { return "gpsslam_b200 0.1 sm_100a"; }
+
+struct gsb_tsdf
+{
+    gsb_tsdf_config_t cfg;
+    tsdf::Scene scene;
+    tsdf::Frame frame;
+    tsdf::Camera cam;      // live camera (pose_d + intrinsics_d)
+    se3::Pose pose_d, pose_pointCloud;
+    cudaStream_t stream, ownStream;
+    // device buffers
+    short *depth_mm;
+    uchar4 *rgba;
+    float *depth_f;
+    float2 *minmaxLive, *minmaxFree;
+    float4 *rayLive, *rayFree, *pointsMap, *normalsMap;
+    uchar4 *imageFree;
+    icp::Tracker *tracker;
+    int framesProcessed;       // ITMBasicEngine::framesProcessed (fused frames)
+    int trackingFrames;        // ITMTrackingState::framesProcessed
+    int agePointCloud;         // ITMTrackingState::age_pointCloud (-1 = no valid point cloud yet)
+    bool haveFrame;
+    std::vector<void *> allocs;
+};
+
+#define E_CUDA(call) GS_CUDA_OK(call)
+
+template <typename T>
+static int dev_alloc(gsb_tsdf *e, T **p, size_t n)
+{
+    E_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    e->allocs.push_back((void *)*p);
+    return 0;
+}
+
+extern "C" void gsb_tsdf_default_config(gsb_tsdf_config_t *c)
+{
+    memset(c, 0, sizeof *c);
+    c->width = 1200, c->height = 680;
+    c->fx = 600.f, c->fy = 600.f, c->cx = 599.5f, c->cy = 339.5f; // configs/release/replica/office0.yaml:18-20
+    c->voxel_size = 0.005f, c->mu = 0.02f, c->view_frustum_min = 0.2f, c->view_frustum_max = 10.0f;
+    c->max_w = 100;
+    c->num_blocks = SDF_DEFAULT_BLOCK_NUM;
+    c->tracker = 0;
+    c->device = 0;
+    c->integrate_variant = 0;
+}
+
+extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
+{
+    if (!cfg || !out)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return gs_set_error(__FILE__, __LINE__, "no CUDA device: gpsslam_b200 has no CPU fallback");
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->voxel_size <= 0 || cfg->mu <= 0)
+        return gs_set_error(__FILE__, __LINE__, "invalid configuration");
+    E_CUDA(cudaSetDevice(cfg->device));
+    gsb_tsdf *e = new (std::nothrow) gsb_tsdf();
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "out of host memory");
+    e->cfg = *cfg;
+    if (e->cfg.num_blocks <= 0)
+        e->cfg.num_blocks = SDF_DEFAULT_BLOCK_NUM;
+    if (e->cfg.max_w <= 0)
+        e->cfg.max_w = 100;
+    const int W = cfg->width, H = cfg->height, P = W * H;
+    tsdf::Scene &s = e->scene;
+    s.E = SDF_TOTAL_ENTRIES;
+    s.numBlocks = e->cfg.num_blocks;
+    s.voxelSize = cfg->voxel_size, s.mu = cfg->mu, s.vfmin = cfg->view_frustum_min, s.vfmax = cfg->view_frustum_max;
+    s.maxW = e->cfg.max_w;
+    E_CUDA(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
+    e->stream = e->ownStream;
+    int rc = 0;
+    rc |= dev_alloc(e, &s.table, (size_t)s.E);
+    rc |= dev_alloc(e, &s.vba, (size_t)s.numBlocks * SDF_BLOCK_SIZE3);
+    rc |= dev_alloc(e, &s.allocKey, (size_t)s.E);
+    rc |= dev_alloc(e, &s.visType, (size_t)s.E);
+    rc |= dev_alloc(e, &s.visIds, (size_t)s.numBlocks);
+    rc |= dev_alloc(e, &s.chunkCounts, (size_t)(s.E + 1023) / 1024);
+    rc |= dev_alloc(e, &s.state, 8);
+    rc |= dev_alloc(e, &e->depth_mm, (size_t)P);
+    rc |= dev_alloc(e, &e->rgba, (size_t)P);
+    rc |= dev_alloc(e, &e->depth_f, (size_t)P);
+    const int mm = ((W + 7) / 8) * ((H + 7) / 8);
+    rc |= dev_alloc(e, &e->minmaxLive, (size_t)mm);
+    rc |= dev_alloc(e, &e->minmaxFree, (size_t)mm);
+    rc |= dev_alloc(e, &e->rayLive, (size_t)P);
+    rc |= dev_alloc(e, &e->rayFree, (size_t)P);
+    rc |= dev_alloc(e, &e->pointsMap, (size_t)P);
+    rc |= dev_alloc(e, &e->normalsMap, (size_t)P);
+    rc |= dev_alloc(e, &e->imageFree, (size_t)P);
+    if (rc)
+    {
+        gsb_tsdf_destroy(e);
+        return 1;
+    }
+    e->frame.depth_mm = e->depth_mm, e->frame.rgba = e->rgba, e->frame.depth_f = e->depth_f, e->frame.W = W, e->frame.H = H;
+    e->cam.fx = cfg->fx, e->cam.fy = cfg->fy, e->cam.cx = cfg->cx, e->cam.cy = cfg->cy;
+    e->tracker = nullptr;
+    if (cfg->tracker != 0)
+    {
+        e->tracker = icp::create_tracker(cfg->tracker, W, H, cfg->view_frustum_min, cfg->view_frustum_max);
+        if (!e->tracker)
+        {
+            gsb_tsdf_destroy(e);
+            return gs_set_error(__FILE__, __LINE__, "tracker creation failed");
+        }
+    }
+    *out = e;
+    return gsb_tsdf_reset(e);
+}
+
+extern "C" void gsb_tsdf_destroy(gsb_tsdf_t *e)
+{
+    if (!e)
+        return;
+    cudaStreamSynchronize(e->stream);
+    if (e->tracker)
+        icp::destroy_tracker(e->tracker);
+    for (void *p : e->allocs)
+        cudaFree(p);
+    cudaStreamDestroy(e->ownStream);
+    delete e;
+}
+
+extern "C" int gsb_tsdf_reset(gsb_tsdf_t *e)
+{
+    tsdf::reset_scene(e->scene, e->stream);
+    const int W = e->cfg.width, H = e->cfg.height, P = W * H;
+    E_CUDA(cudaMemsetAsync(e->rayLive, 0, sizeof(float4) * P, e->stream));
+    E_CUDA(cudaMemsetAsync(e->rayFree, 0, sizeof(float4) * P, e->stream));
+    E_CUDA(cudaMemsetAsync(e->pointsMap, 0, sizeof(float4) * P, e->stream));
+    E_CUDA(cudaMemsetAsync(e->normalsMap, 0, sizeof(float4) * P, e->stream));
+    E_CUDA(cudaMemsetAsync(e->imageFree, 0, sizeof(uchar4) * P, e->stream));
+    e->pose_d = se3::Pose();
+    e->pose_pointCloud = se3::Pose();
+    e->cam.M = e->pose_d.M;
+    e->cam.invM = e->pose_d.get_invM();
+    e->framesProcessed = 0;
+    e->trackingFrames = 0;
+    e->agePointCloud = -1;
+    e->haveFrame = false;
+    E_CUDA(cudaStreamSynchronize(e->stream));
+    E_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_tsdf_set_stream(gsb_tsdf_t *e, void *st)
+{
+    e->stream = st ? (cudaStream_t)st : e->ownStream;
+    return 0;
+}
+extern "C" void *gsb_tsdf_get_stream(gsb_tsdf_t *e) { return (void *)e->stream; }
+extern "C" int gsb_tsdf_sync(gsb_tsdf_t *e)
+{
+    E_CUDA(cudaStreamSynchronize(e->stream));
+    E_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void refresh_camera(gsb_tsdf *e)
+{
+    e->cam.M = e->pose_d.M;
+    e->cam.invM = e->pose_d.get_invM();
+}
+
+// stages after the view is on the device
+static int process_resident(gsb_tsdf *e, const float *gt_c2w)
+{
+    cudaStream_t st = e->stream;
+    // --- tracking (ITMBasicEngine.tpp:273-280)
+    if (e->cfg.tracker == 0)
+    {
+        if (!gt_c2w)
+            return gs_set_error(__FILE__, __LINE__, "tracker == 0 needs a ground-truth camera-to-world pose");
+        Mat4 c2w;
+        memcpy(c2w.m, gt_c2w, 64);
+        e->pose_d.set_invM(c2w);
+        e->pose_d.coerce();
+    }
+    else
+    {
+        // ITMTrackingController::Track -> tracker->TrackCamera; needs this frame's float depth, which the
+        // reference produces in UpdateView.  Ours is produced by the allocation pass, so convert first.
+        if (e->agePointCloud != -1)
+        {
+            if (e->agePointCloud >= 0)
+                e->trackingFrames++;
+            else
+                e->trackingFrames = 0;
+            icp::convert_depth(e->depth_mm, e->depth_f, e->cfg.width, e->cfg.height, st);
+            Mat4 scenePose = e->pose_pointCloud.M;
+            int rc = icp::track_camera(e->tracker, e->depth_f, e->pointsMap, e->normalsMap, e->cam.fx, e->cam.fy, e->cam.cx, e->cam.cy, scenePose,
+                                       e->trackingFrames, &e->pose_d, st);
+            if (rc)
+                return rc;
+        }
+    }
+    refresh_camera(e);
+    // --- fusion (ITMDenseMapper::ProcessFrame)
+    tsdf::allocate(e->scene, e->frame, e->cam, st);
+    tsdf::integrate(e->scene, e->frame, e->cam, e->cfg.integrate_variant, st);
+    e->framesProcessed++;
+    // --- ITMTrackingController::Prepare (always: requiresPointCloudRendering() is constant true)
+    const int W = e->cfg.width, H = e->cfg.height;
+    tsdf::expected_depth_live(e->scene, e->cam, W, H, e->minmaxLive, st);
+    tsdf::raycast(e->scene, e->cam, W, H, e->minmaxLive, e->rayLive, nullptr, true, st);
+    tsdf::icp_maps(e->scene, e->cam, W, H, e->rayLive, e->pointsMap, e->normalsMap, st);
+    e->pose_pointCloud = e->pose_d;
+    e->agePointCloud = (e->agePointCloud == -1) ? -2 : 0;
+    e->haveFrame = true;
+    E_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_tsdf_process_frame(gsb_tsdf_t *e, const uint8_t *rgba_host, const int16_t *depth_mm_host, const float *gt_c2w)
+{
+    if (!e || !rgba_host || !depth_mm_host)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    const size_t P = (size_t)e->cfg.width * e->cfg.height;
+    // B1: ITMViewBuilder::UpdateView H2D (ITMViewBuilder_CUDA.cu:60-61); async when the host buffers are pinned
+    E_CUDA(cudaMemcpyAsync(e->rgba, rgba_host, P * 4, cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(cudaMemcpyAsync(e->depth_mm, depth_mm_host, P * 2, cudaMemcpyHostToDevice, e->stream));
+    return process_resident(e, gt_c2w);
+}
+
+extern "C" int gsb_tsdf_process_frame_device(gsb_tsdf_t *e, const void *rgba_dev, const void *depth_mm_dev, const float *gt_c2w)
+{
+    if (!e || !rgba_dev || !depth_mm_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    e->frame.rgba = (const uchar4 *)rgba_dev;
+    e->frame.depth_mm = (const short *)depth_mm_dev;
+    int rc = process_resident(e, gt_c2w);
+    e->frame.rgba = e->rgba;
+    e->frame.depth_mm = e->depth_mm;
+    return rc;
+}
+
+extern "C" int gsb_tsdf_run_raycast(gsb_tsdf_t *e, const float *c2w, float fx, float fy, float cx, float cy)
+{
+    if (!e || !c2w)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    // slam_pipeline.cpp:373-380 builds an SE3Pose with SetInvM(c2w); runRaycast then uses pose->GetM() / GetInvM()
+    se3::Pose p;
+    Mat4 m;
+    memcpy(m.m, c2w, 64);
+    p.set_invM(m);
+    tsdf::Camera cam;
+    cam.M = p.M;
+    cam.invM = p.get_invM();
+    cam.fx = fx, cam.fy = fy, cam.cx = cx, cam.cy = cy;
+    const int W = e->cfg.width, H = e->cfg.height;
+    tsdf::expected_depth_free(e->scene, cam, W, H, e->minmaxFree, e->stream);
+    tsdf::raycast(e->scene, cam, W, H, e->minmaxFree, e->rayFree, e->imageFree, false, e->stream);
+    E_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" const void *gsb_tsdf_free_image_dev(gsb_tsdf_t *e) { return e->imageFree; }
+extern "C" const void *gsb_tsdf_free_vertex_dev(gsb_tsdf_t *e) { return e->rayFree; }
+extern "C" const void *gsb_tsdf_live_vertex_dev(gsb_tsdf_t *e) { return e->rayLive; }
+extern "C" const void *gsb_tsdf_points_map_dev(gsb_tsdf_t *e) { return e->pointsMap; }
+extern "C" const void *gsb_tsdf_normals_map_dev(gsb_tsdf_t *e) { return e->normalsMap; }
+
+extern "C" int gsb_tsdf_get_pose(gsb_tsdf_t *e, float *M, float *invM)
+{
+    if (M)
+        memcpy(M, e->pose_d.M.m, 64);
+    if (invM)
+    {
+        Mat4 i = e->pose_d.get_invM();
+        memcpy(invM, i.m, 64);
+    }
+    return 0;
+}
+extern "C" float gsb_tsdf_voxel_size(gsb_tsdf_t *e) { return e->cfg.voxel_size; }
+extern "C" int gsb_tsdf_frames_processed(gsb_tsdf_t *e) { return e->framesProcessed; }
+
+extern "C" int gsb_tsdf_counter(gsb_tsdf_t *e, int which, int *value)
+{
+    if (which < 0 || which > 3)
+        return gs_set_error(__FILE__, __LINE__, "bad counter id");
+    E_CUDA(cudaMemcpyAsync(value, e->scene.state + which, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    E_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int gsb_tsdf_read(gsb_tsdf_t *e, int what, void *dst, size_t bytes)
+{
+    const size_t P = (size_t)e->cfg.width * e->cfg.height;
+    const size_t mm = (size_t)((e->cfg.width + 7) / 8) * ((e->cfg.height + 7) / 8);
+    const void *src = nullptr;
+    size_t avail = 0;
+    switch (what)
+    {
+    case GSB_TSDF_HASH_TABLE: src = e->scene.table, avail = (size_t)e->scene.E * 16; break;
+    case GSB_TSDF_VOXELS: src = e->scene.vba, avail = (size_t)e->scene.numBlocks * SDF_BLOCK_SIZE3 * 8; break;
+    case GSB_TSDF_VISIBLE_IDS: src = e->scene.visIds, avail = (size_t)e->scene.numBlocks * 4; break;
+    case GSB_TSDF_VISIBLE_TYPES: src = e->scene.visType, avail = (size_t)e->scene.E; break;
+    case GSB_TSDF_DEPTH_F: src = e->depth_f, avail = P * 4; break;
+    case GSB_TSDF_MINMAX_LIVE: src = e->minmaxLive, avail = mm * 8; break;
+    case GSB_TSDF_MINMAX_FREE: src = e->minmaxFree, avail = mm * 8; break;
+    case GSB_TSDF_RAYCAST_LIVE: src = e->rayLive, avail = P * 16; break;
+    case GSB_TSDF_RAYCAST_FREE: src = e->rayFree, avail = P * 16; break;
+    case GSB_TSDF_POINTS_MAP: src = e->pointsMap, avail = P * 16; break;
+    case GSB_TSDF_NORMALS_MAP: src = e->normalsMap, avail = P * 16; break;
+    case GSB_TSDF_IMAGE_FREE: src = e->imageFree, avail = P * 4; break;
+    default: return gs_set_error(__FILE__, __LINE__, "bad read id");
+    }
+    if (bytes > avail)
+        return gs_set_error(__FILE__, __LINE__, "read larger than the buffer");
+    E_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    E_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage)
+{
+    if (!e->haveFrame)
+        return gs_set_error(__FILE__, __LINE__, "run_stage needs a processed frame");
+    const int W = e->cfg.width, H = e->cfg.height;
+    switch (stage)
+    {
+    case 0: tsdf::allocate(e->scene, e->frame, e->cam, e->stream); break;
+    case 1: tsdf::integrate(e->scene, e->frame, e->cam, e->cfg.integrate_variant, e->stream); break;
+    case 2: tsdf::expected_depth_live(e->scene, e->cam, W, H, e->minmaxLive, e->stream); break;
+    case 3: tsdf::raycast(e->scene, e->cam, W, H, e->minmaxLive, e->rayLive, nullptr, true, e->stream); break;
+    case 4: tsdf::icp_maps(e->scene, e->cam, W, H, e->rayLive, e->pointsMap, e->normalsMap, e->stream); break;
+    default: return gs_set_error(__FILE__, __LINE__, "bad stage id");
+    }
+    E_CUDA(cudaGetLastError());
+    return 0;
+}
