@@ -96,3 +96,7 @@ GS_D HashEntry load_entry_cg(const HashEntry *table, int idx)
     } while (0)
 
 int gs_set_error(const char *file, int line, const char *msg);
+
+// number of kernels this library has launched (read through gsb_launch_count(); bench.py reports it as gpu_launches)
+extern long long g_gsb_launches;
+#define GS_COUNT_LAUNCHES(n) (g_gsb_launches += (n))

@@ -23,6 +23,8 @@ int gs_set_error(const char *file, int line, const char *msg)
     return 1;
 }
 extern "C" const char *gsb_last_error(void) { return g_err.c_str(); }
+long long g_gsb_launches = 0;
+extern "C" long long gsb_launch_count(void) { return g_gsb_launches; }
 extern "C" const char *gsb_version(void) { return "gpsslam_b200 0.1 sm_100a"; }
 
 struct gsb_tsdf

