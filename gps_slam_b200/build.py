@@ -17,6 +17,9 @@ SOURCES = [
     ("tsdf_kernels.cu", ["-fmad=false"]),
     ("tsdf_engine.cu", ["-fmad=false"]),
     ("icp_kernels.cu", ["-fmad=false"]),
+    ("gs_project.cu", ["-fmad=false"]),
+    ("gs_raster.cu", []),
+    ("gs_engine.cu", ["-fmad=false"]),
 ]
 
 

@@ -1,6 +1,6 @@
 // Internal interface of the gsplat-GES path: kernels in gs_project.cu (built with
-// -fmad=false: projection / SH / binning / parameter backward + Adam) and gs_raster.cu (rasteriser forward / backward),
-// model object and C ABI in gs_engine.cu.
+// -fmad=false: projection / SH / binning / parameter backward + Adam / prune / spawn) and gs_raster.cu (rasteriser
+// forward / backward), model object and C ABI in gs_engine.cu.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,15 +12,15 @@ namespace gs
 
 // Packed per-splat record produced by the projection pass and consumed by binning and both rasteriser passes.
 // 48 B = 3 x float4, so one splat is three 16-byte transactions wherever it is gathered.
-//   q0 = (mean2d.x, mean2d.y, opacity, int_as_float(radius))      radius = 0 -> culled
+//   q0 = (mean2d.x, mean2d.y, opacity, int_as_float(radius))      radius = 0 -> culled (rest of the record undefined)
 //   q1 = (conic.a,  conic.b,  conic.c, camera depth)
-//   q2 = (r, g, b, int_as_float(bit c set <=> raw SH colour c + 0.5 >= 0))
+//   q2 = (r, g, b, int_as_float(bit c set <=> raw SH colour c + 0.5 >= 0  |  bit 8 set <=> more than one backward item))
 struct __align__(16) SplatRec
 {
     float4 q0, q1, q2;
 };
 
-// Raster-side gradient per splat (zeroed by the projection pass, accumulated by the raster backward)
+// Raster-side gradient per splat
 //   g0 = (v_mean2d.x, v_mean2d.y, v_opacity, v_depth)   g1 = (v_conic.a, v_conic.b, v_conic.c, 0)   g2 = (v_r, v_g, v_b, 0)
 struct __align__(16) SplatGrad
 {
@@ -29,18 +29,12 @@ struct __align__(16) SplatGrad
 
 struct ParamPtrs
 {
-    float *means;     // [N,3]
-    float *scales;    // [N,3] log
-    float *quats;     // [N,4] w x y z
-    float *dc;        // [N,3]
-    float *rest;      // [N,15,3]
-    float *opac;      // [N,1] logit
-};
-
-struct AdamState
-{
-    ParamPtrs m, v;
-    unsigned char *touched; // [N] 1 once a Gaussian received a gradient in this optimiser cycle
+    float *means;  // [N,3]
+    float *scales; // [N,3] log
+    float *quats;  // [N,4] w x y z
+    float *dc;     // [N,3]
+    float *rest;   // [N,15,3]
+    float *opac;   // [N] logit
 };
 
 struct AdamStep
@@ -49,71 +43,90 @@ struct AdamStep
     float step_size[6]; // lr / bias_correction1 for means, scales, quats, dc, rest, opac
 };
 
-struct BinBuffers
+// counters[] layout
+enum
 {
-    int *tileCount;    // [T+1]
-    int *tileOffsets;  // [T+1] exclusive scan; [T] = n_isects
-    int *tileCursor;   // [T]
-    int *flattenIds;   // [isectCap]
-    int isectCap;
-    int *counters;     // [8]: 0 n_isects, 1 n_bwd_items, 2 overflow flag, 3 n_visible
+    CNT_ISECTS = 0,   // n_isects of the current binning (clamped to the capacity)
+    CNT_ITEMS = 1,    // number of backward work items of the current projection
+    CNT_OVERFLOW = 2, // bit 0: intersections exceeded isectCap, bit 1: backward items exceeded itemCap, bit 2: Gaussian capacity
+    CNT_VISIBLE = 3,  // running count of Gaussians with radius > 0 (moved to CNT_VISIBLE_LAST by the binning pass)
+    CNT_VISIBLE_LAST = 4,
+    CNT_SCRATCH = 5,  // prune / spawn scratch (3 ints)
+    CNT_TOTAL = 8
 };
 
-struct BwdItems
+struct Bins
 {
-    int2 *items;       // (gaussian id, chunk index)
-    int cap;
+    int *tileCount;     // [T+1] zero between iterations
+    int *tileOffsets;   // [T+1] exclusive scan; [T] = n_isects
+    int *tileCursor;    // [T]
+    int *flatten;       // [isectCap] scatter order (arbitrary within a tile)
+    int *flattenSorted; // [isectCap] ascending Gaussian id within each tile  == reference flatten_ids
+    int isectCap;
+    int2 *items;        // [itemCap] (gaussian id, chunk of BWD_GROUPS_PER_ITEM pixel groups)
+    int itemCap;
+    int *counters;      // [CNT_TOTAL]
 };
 
 enum RasterMode
 {
-    RASTER_RAW = 0,    // write render_colors [H,W,4] + alphas [H,W]           (gsplat::rasterize_to_pixels_fwd_ges_tensor)
-    RASTER_RENDER = 1, // write composited rgb [H,W,3], depth [H,W], alpha     (RawGaussianModel::gesForward outputs)
+    RASTER_RAW = 0,    // render_colors [H,W,4] + alphas [H,W]                 (gsplat::rasterize_to_pixels_fwd_ges_tensor)
+    RASTER_RENDER = 1, // composited rgb [H,W,3], depth [H,W], alpha [H,W]      (RawGaussianModel::gesForward outputs)
     RASTER_TRAIN = 2   // composite + L1 loss + dL/d(render) packed as float4   (gesForward + computeLoss + backward head)
 };
 
-struct RasterOut
+struct RasterIO
 {
-    float *render4;   // RAW
-    float *alphas;    // RAW / RENDER
-    float *rgb;       // RENDER
-    float *depth;     // RENDER
-    float4 *v_out;    // TRAIN: (v_r, v_g, v_b, v_alpha)
-    double *loss;     // TRAIN: sum |rgb - gt| (divide by 3P)
+    const float *refDepth;  // [H,W] TSDF raycast depth (raw; < 0.01 means "no hit")
+    const float *baseColor; // [H,W,3] TSDF raycast colour
+    const float *gt;        // [H,W,3] TRAIN
+    float deltaDepth;
+    int clampRef;           // 1: refDepth < 0.01 -> 1000 inside the kernel (src/raw_gs_model.cpp:207); 0: use as given
+    float *render4;         // RAW
+    float *alphas;          // RAW / RENDER
+    float *rgb;             // RENDER
+    float *depth;           // RENDER
+    float4 *v_out;          // TRAIN: (v_render_r, v_render_g, v_render_b, v_render_alpha)
+    float *lossTile;        // TRAIN: per-tile sum |rgb - gt|
 };
 
 constexpr int TILE = 16;
 constexpr int BWD_GROUPS_PER_ITEM = 64;
+constexpr int PARAMS_PER_GAUSSIAN = 59;
 
 // ---- gs_project.cu
-void project_sh_fwd(const ParamPtrs &p, int N, const CamParams &cam, SplatRec *recs, SplatGrad *grads, const BinBuffers &bins, int tileW, int tileH,
-                    const BwdItems &items, bool forBackward, cudaStream_t st);
-void bin_tiles(const SplatRec *recs, int N, const BinBuffers &bins, int tileW, int tileH, cudaStream_t st);
-void bwd_params_adam(const ParamPtrs &p, const AdamState &s, const AdamStep &step, int N, const CamParams &cam, const SplatRec *recs,
-                     const SplatGrad *grads, cudaStream_t st);
-// staged pieces (gsplat::*_tensor shaped)
+void project_sh_fwd(const ParamPtrs &p, const int *nDev, int nUpper, const CamParams &cam, SplatRec *recs, SplatGrad *grads, const Bins &bins,
+                    int tileW, int tileH, bool forBackward, cudaStream_t st);
+void bin_tiles(const SplatRec *recs, const int *nDev, int nUpper, const Bins &bins, int tileW, int tileH, cudaStream_t st);
+// dbg: optional dump of the parameter gradients (same layout as the parameters); nullptr in production
+void bwd_params_adam(const ParamPtrs &p, const ParamPtrs &m, const ParamPtrs &v, unsigned char *touched, const AdamStep &step, const int *nDev,
+                     int nUpper, const CamParams &cam, const SplatRec *recs, const SplatGrad *grads, const ParamPtrs *dbg, int *counters,
+                     cudaStream_t st);
+void reduce_loss(const float *lossTile, int T, double scale, double *out, cudaStream_t st);
+// removeRedundantGs + prunePoints: stable compaction of parameters (Adam state is re-created by the next cycle)
+void prune(const ParamPtrs &p, const ParamPtrs &tmp, int *nDev, int nUpper, float minOpac, float minScale, float maxScale, int *scanTmp,
+           int *counters, cudaStream_t st);
+
+// staged pieces with the argument layout of the reference's gsplat::*_tensor functions (C = 1)
 void staged_project_fwd(int N, const float *means, const float *quats, const float *scales, const CamParams &cam, int *radii, float *means2d,
                         float *depths, float *conics, cudaStream_t st);
-void staged_sh_fwd(int N, const float *dirs, const float *coeffs, const unsigned char *mask, float *colors, cudaStream_t st);
-void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *opac, const int *radii, SplatRec *recs,
-                 cudaStream_t st);
-void staged_count_tiles(const SplatRec *recs, int N, const BinBuffers &bins, int tileW, int tileH, int *tilesPerGauss, cudaStream_t st);
-void staged_fill_isect_ids(const BinBuffers &bins, int T, long long *isectIds, cudaStream_t st);
-void staged_offset_encode(const long long *isectIds, int nIsects, int T, int *offsets, cudaStream_t st);
-void staged_sh_bwd(int N, const float *dirs, const float *coeffs, const unsigned char *mask, const float *v_colors, float *v_coeffs, float *v_dirs,
-                   cudaStream_t st);
 void staged_project_bwd(int N, const float *means, const float *quats, const float *scales, const CamParams &cam, const int *radii,
                         const float *conics, const float *v_means2d, const float *v_depths, const float *v_conics, float *v_means, float *v_quats,
                         float *v_scales, cudaStream_t st);
+void staged_sh_fwd(int N, const float *dirs, const float *coeffs, const unsigned char *mask, float *colors, cudaStream_t st);
+void staged_sh_bwd(int N, const float *dirs, const float *coeffs, const unsigned char *mask, const float *v_colors, float *v_coeffs, float *v_dirs,
+                   cudaStream_t st);
+void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *opac, const int *radii, SplatRec *recs,
+                 SplatGrad *grads, const Bins &bins, int tileW, int tileH, int *tilesPerGauss, bool forBackward, cudaStream_t st);
+void staged_isect_ids(const Bins &bins, int T, long long *isectIds, cudaStream_t st);
+void staged_unpack_grads(int N, const SplatRec *recs, const SplatGrad *grads, float *v_means2d, float *v_conics, float *v_colors4, float *v_opac,
+                         cudaStream_t st);
 void staged_adam(int n, float *p, const float *g, float *m, float *v, const AdamScalars &a, float step_size, cudaStream_t st);
-void staged_unpack_grads(int N, const SplatGrad *grads, float *v_means2d, float *v_conics, float *v_colors4, float *v_opac, cudaStream_t st);
-void build_bwd_items(const SplatRec *recs, int N, const BinBuffers &bins, const BwdItems &items, SplatGrad *grads, cudaStream_t st);
 
 // ---- gs_raster.cu
-void raster_fwd(int mode, const SplatRec *recs, const BinBuffers &bins, int W, int H, int tileW, int tileH, const float *refDepth, bool clampRef,
-                const float *baseColor, const float *gt, float deltaDepth, const RasterOut &out, cudaStream_t st);
-void raster_bwd(const SplatRec *recs, const BinBuffers &bins, const BwdItems &items, int W, int H, const float *refDepth, bool clampRef,
-                float deltaDepth, const float4 *v_out, const float *v_depth /* nullable */, SplatGrad *grads, cudaStream_t st);
+void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
+void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth /* nullable [H,W] */,
+                SplatGrad *grads, cudaStream_t st);
 void pack_v_out(int P, const float *v_render4, const float *v_alphas, float4 *v_out, float *v_depth, cudaStream_t st);
 
 } // namespace gs

@@ -1,0 +1,423 @@
+// Gaussian model object + its C ABI (include/gpsslam_b200.h, section A).
+// Host logic mirrors RawGaussianModel / SLAMGaussianModel (reference include/raw_gs_model.h:8-298, src/raw_gs_model.cpp:188-417,
+// 654-705; slam/slam_gs_model.cpp:5-56) for the GES render method: gesForward, computeLoss, backward, optimizersStep,
+// initOptimizers, prunePoints, add.  One training iteration is 7 asynchronous launches on one stream with no host round trip
+// (the reference: ~40-60 launches and 3 host syncs).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/gpsslam_b200.h"
+#include "common.cuh"
+#include "gs.h"
+
+using namespace gs;
+
+struct gsb_gs
+{
+    gsb_gs_config_t cfg;
+    cudaStream_t stream, ownStream;
+    int W, H, tileW, tileH, T;
+    int cap;         // Gaussian capacity
+    int nUpper;      // host-side upper bound of the Gaussian count (exact after gsb_gs_count)
+    int *nDev;       // device-side exact count
+    ParamPtrs p, tmp, m, v, dbg;
+    unsigned char *touched;
+    SplatRec *recs;
+    SplatGrad *grads;
+    Bins bins;
+    float4 *v_out;
+    float *v_depth;
+    float *lossTile;
+    double *lossDev;
+    int *scanTmp;
+    int adamStep;
+    int *hostInts;   // pinned [8]
+    double *hostLoss; // pinned
+    bool haveDbg;
+    std::vector<void *> allocs;
+};
+
+template <typename T>
+static int dev_alloc(gsb_gs *e, T **p, size_t n)
+{
+    GS_CUDA_OK(cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)));
+    e->allocs.push_back((void *)*p);
+    return 0;
+}
+
+static int alloc_params(gsb_gs *e, ParamPtrs &q, size_t cap)
+{
+    int rc = 0;
+    rc |= dev_alloc(e, &q.means, cap * 3);
+    rc |= dev_alloc(e, &q.scales, cap * 3);
+    rc |= dev_alloc(e, &q.quats, cap * 4);
+    rc |= dev_alloc(e, &q.dc, cap * 3);
+    rc |= dev_alloc(e, &q.rest, cap * 45);
+    rc |= dev_alloc(e, &q.opac, cap);
+    return rc;
+}
+
+extern "C" void gsb_gs_default_config(gsb_gs_config_t *c)
+{
+    memset(c, 0, sizeof *c);
+    c->width = 1200, c->height = 680;
+    c->capacity = 1 << 21;
+    c->isect_capacity = 1 << 24;
+    c->item_capacity = 1 << 23;
+    c->max_gs_radii = 100;        // MODEL.max_gs_radii      (configs/release/replica/office0.yaml:83)
+    c->delta_depth = 0.1f;        // MODEL.delta_depth
+    c->eps2d = 0.3f, c->near_plane = 0.01f, c->far_plane = 1e10f, c->radius_clip = 0.0f; // include/raw_gs_model.h defaults
+    c->lr_means = 0.00016f, c->lr_scales = 0.005f, c->lr_quats = 0.001f, c->lr_dc = 0.0025f, c->lr_rest = 0.0005f, c->lr_opac = 0.05f;
+    c->scene_scale = 1.0f;
+    c->device = 0;
+}
+
+extern "C" void gsb_gs_destroy(gsb_gs_t *e)
+{
+    if (!e)
+        return;
+    cudaStreamSynchronize(e->stream);
+    for (void *q : e->allocs)
+        cudaFree(q);
+    if (e->hostInts)
+        cudaFreeHost(e->hostInts);
+    if (e->hostLoss)
+        cudaFreeHost(e->hostLoss);
+    cudaStreamDestroy(e->ownStream);
+    delete e;
+}
+
+extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
+{
+    if (!cfg || !out)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return gs_set_error(__FILE__, __LINE__, "no CUDA device: gpsslam_b200 has no CPU fallback");
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->capacity <= 0)
+        return gs_set_error(__FILE__, __LINE__, "invalid configuration");
+    GS_CUDA_OK(cudaSetDevice(cfg->device));
+    gsb_gs *e = new (std::nothrow) gsb_gs();
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "out of host memory");
+    e->cfg = *cfg;
+    e->W = cfg->width, e->H = cfg->height;
+    e->tileW = (e->W + TILE - 1) / TILE, e->tileH = (e->H + TILE - 1) / TILE, e->T = e->tileW * e->tileH;
+    e->cap = (cfg->capacity + 127) / 128 * 128;
+    e->nUpper = 0;
+    e->adamStep = 0;
+    e->haveDbg = false;
+    e->hostInts = nullptr, e->hostLoss = nullptr;
+    GS_CUDA_OK(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
+    e->stream = e->ownStream;
+    const size_t P = (size_t)e->W * e->H;
+    int rc = 0;
+    rc |= alloc_params(e, e->p, e->cap);
+    rc |= alloc_params(e, e->tmp, e->cap);
+    rc |= alloc_params(e, e->m, e->cap);
+    rc |= alloc_params(e, e->v, e->cap);
+    memset(&e->dbg, 0, sizeof e->dbg);
+    rc |= dev_alloc(e, &e->touched, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->recs, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->grads, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->nDev, 1);
+    e->bins.isectCap = cfg->isect_capacity > 0 ? cfg->isect_capacity : (1 << 24);
+    e->bins.itemCap = cfg->item_capacity > 0 ? cfg->item_capacity : (1 << 23);
+    rc |= dev_alloc(e, &e->bins.tileCount, (size_t)e->T + 1);
+    rc |= dev_alloc(e, &e->bins.tileOffsets, (size_t)e->T + 1);
+    rc |= dev_alloc(e, &e->bins.tileCursor, (size_t)e->T + 1);
+    rc |= dev_alloc(e, &e->bins.flatten, (size_t)e->bins.isectCap);
+    rc |= dev_alloc(e, &e->bins.flattenSorted, (size_t)e->bins.isectCap);
+    rc |= dev_alloc(e, &e->bins.items, (size_t)e->bins.itemCap);
+    rc |= dev_alloc(e, &e->bins.counters, (size_t)CNT_TOTAL);
+    rc |= dev_alloc(e, &e->v_out, P);
+    rc |= dev_alloc(e, &e->v_depth, P);
+    rc |= dev_alloc(e, &e->lossTile, (size_t)e->T);
+    rc |= dev_alloc(e, &e->lossDev, 1);
+    rc |= dev_alloc(e, &e->scanTmp, (size_t)e->cap / 1024 + 2);
+    if (!rc && cudaMallocHost((void **)&e->hostInts, 8 * sizeof(int)) != cudaSuccess)
+        rc = gs_set_error(__FILE__, __LINE__, "pinned allocation failed");
+    if (!rc && cudaMallocHost((void **)&e->hostLoss, sizeof(double)) != cudaSuccess)
+        rc = gs_set_error(__FILE__, __LINE__, "pinned allocation failed");
+    if (rc)
+    {
+        gsb_gs_destroy(e);
+        return 1;
+    }
+    cudaMemsetAsync(e->nDev, 0, sizeof(int), e->stream);
+    cudaMemsetAsync(e->bins.tileCount, 0, sizeof(int) * (e->T + 1), e->stream);
+    cudaMemsetAsync(e->bins.counters, 0, sizeof(int) * CNT_TOTAL, e->stream);
+    cudaMemsetAsync(e->touched, 0, (size_t)e->cap, e->stream);
+    cudaMemsetAsync(e->lossTile, 0, sizeof(float) * e->T, e->stream);
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return 0;
+}
+
+extern "C" int gsb_gs_set_stream(gsb_gs_t *e, void *st)
+{
+    e->stream = st ? (cudaStream_t)st : e->ownStream;
+    return 0;
+}
+extern "C" int gsb_gs_sync(gsb_gs_t *e)
+{
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// exact Gaussian count (one 4-byte D2H + stream sync); also tightens the host-side launch bound
+extern "C" int gsb_gs_count(gsb_gs_t *e, int *n)
+{
+    GS_CUDA_OK(cudaMemcpyAsync(e->hostInts, e->nDev, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->nUpper = e->hostInts[0];
+    if (n)
+        *n = e->hostInts[0];
+    return 0;
+}
+extern "C" int gsb_gs_count_upper(gsb_gs_t *e) { return e->nUpper; }
+
+static int copy_rows(gsb_gs *e, float *dst, const float *src, size_t n, size_t width, size_t dstRow)
+{
+    if (!src || n == 0)
+        return 0;
+    GS_CUDA_OK(cudaMemcpyAsync(dst + dstRow * width, src, n * width * sizeof(float), cudaMemcpyDefault, e->stream));
+    return 0;
+}
+
+// RawGaussianParams::add (src/raw_gs_param.cpp:123-140): append n Gaussians. Pointers may be host or device (UVA).
+// rest may be NULL (zeros, as RawGaussianParams::init produces).  `at` < 0 appends at the current host-side count.
+static int put_params(gsb_gs *e, int at, int n, const float *means, const float *scales_log, const float *quats, const float *dc, const float *rest,
+                      const float *opac_logit)
+{
+    if (at + n > e->cap)
+        return gs_set_error(__FILE__, __LINE__, "Gaussian capacity exceeded");
+    int rc = 0;
+    rc |= copy_rows(e, e->p.means, means, n, 3, at);
+    rc |= copy_rows(e, e->p.scales, scales_log, n, 3, at);
+    rc |= copy_rows(e, e->p.quats, quats, n, 4, at);
+    rc |= copy_rows(e, e->p.dc, dc, n, 3, at);
+    if (rest)
+        rc |= copy_rows(e, e->p.rest, rest, n, 45, at);
+    else if (n > 0)
+        GS_CUDA_OK(cudaMemsetAsync(e->p.rest + (size_t)at * 45, 0, (size_t)n * 45 * sizeof(float), e->stream));
+    rc |= copy_rows(e, e->p.opac, opac_logit, n, 1, at);
+    return rc;
+}
+
+extern "C" int gsb_gs_set_params(gsb_gs_t *e, int n, const float *means, const float *scales_log, const float *quats, const float *dc,
+                                 const float *rest, const float *opac_logit)
+{
+    if (n < 0 || n > e->cap)
+        return gs_set_error(__FILE__, __LINE__, "Gaussian capacity exceeded");
+    if (put_params(e, 0, n, means, scales_log, quats, dc, rest, opac_logit))
+        return 1;
+    e->hostInts[1] = n;
+    GS_CUDA_OK(cudaMemcpyAsync(e->nDev, &e->hostInts[1], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->nUpper = n;
+    return 0;
+}
+
+extern "C" int gsb_gs_append(gsb_gs_t *e, int n, const float *means, const float *scales_log, const float *quats, const float *dc,
+                             const float *rest, const float *opac_logit)
+{
+    int cur = 0;
+    if (gsb_gs_count(e, &cur))
+        return 1;
+    if (put_params(e, cur, n, means, scales_log, quats, dc, rest, opac_logit))
+        return 1;
+    // new Gaussians have no optimiser state
+    if (n > 0)
+        GS_CUDA_OK(cudaMemsetAsync(e->touched + cur, 0, (size_t)n, e->stream));
+    e->hostInts[1] = cur + n;
+    GS_CUDA_OK(cudaMemcpyAsync(e->nDev, &e->hostInts[1], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->nUpper = cur + n;
+    return 0;
+}
+
+extern "C" int gsb_gs_get_params(gsb_gs_t *e, int n, float *means, float *scales_log, float *quats, float *dc, float *rest, float *opac_logit)
+{
+    if (n > e->cap)
+        return gs_set_error(__FILE__, __LINE__, "read larger than the capacity");
+    struct
+    {
+        float *dst;
+        const float *src;
+        size_t w;
+    } a[6] = {{means, e->p.means, 3}, {scales_log, e->p.scales, 3}, {quats, e->p.quats, 4}, {dc, e->p.dc, 3}, {rest, e->p.rest, 45}, {opac_logit, e->p.opac, 1}};
+    for (auto &x : a)
+        if (x.dst && n > 0)
+            GS_CUDA_OK(cudaMemcpyAsync(x.dst, x.src, (size_t)n * x.w * sizeof(float), cudaMemcpyDefault, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// RawGaussianModel::initOptimizers (src/raw_gs_model.cpp:654-675): the 6 Adam optimisers are re-created, i.e. step = 0, m = v = 0.
+// State is materialised lazily (see k_bwd_params_adam), so this only clears one byte per Gaussian.
+extern "C" int gsb_gs_init_optimizers(gsb_gs_t *e)
+{
+    e->adamStep = 0;
+    if (e->nUpper > 0)
+        GS_CUDA_OK(cudaMemsetAsync(e->touched, 0, (size_t)e->nUpper, e->stream));
+    return 0;
+}
+
+extern "C" int gsb_gs_set_learning_rates(gsb_gs_t *e, float means, float scales, float quats, float dc, float rest, float opac)
+{
+    e->cfg.lr_means = means, e->cfg.lr_scales = scales, e->cfg.lr_quats = quats, e->cfg.lr_dc = dc, e->cfg.lr_rest = rest, e->cfg.lr_opac = opac;
+    return 0;
+}
+
+// c2w: row-major 4x4 camera-to-world (cam.c2w_slam). viewmat = poseInv(c2w) (src/tensor_math.cpp:56-67), fp32, same order as the oracle.
+static void make_camera(const gsb_gs *e, const float *c2w, float fx, float fy, float cx, float cy, CamParams &c)
+{
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            c.R[i * 3 + j] = c2w[j * 4 + i];
+    const float T[3] = {c2w[3], c2w[7], c2w[11]};
+    for (int i = 0; i < 3; i++)
+    {
+        float a = -c.R[i * 3 + 0], b = -c.R[i * 3 + 1], d = -c.R[i * 3 + 2];
+        volatile float s = a * T[0];
+        volatile float s2 = b * T[1];
+        volatile float s3 = s + s2;
+        volatile float s4 = d * T[2];
+        c.t[i] = s3 + s4;
+        c.cam_pos[i] = T[i];
+    }
+    c.fx = fx, c.fy = fy, c.cx = cx, c.cy = cy;
+    c.W = e->W, c.H = e->H;
+    c.eps2d = e->cfg.eps2d, c.near_plane = e->cfg.near_plane, c.far_plane = e->cfg.far_plane, c.radius_clip = e->cfg.radius_clip;
+    c.max_radii = e->cfg.max_gs_radii;
+    cam_limits(c);
+}
+
+static RasterIO make_io(const gsb_gs *e, const float *ref_depth, const float *base_color, const float *gt)
+{
+    RasterIO io;
+    memset(&io, 0, sizeof io);
+    io.refDepth = ref_depth, io.baseColor = base_color, io.gt = gt;
+    io.deltaDepth = e->cfg.delta_depth;
+    io.clampRef = 1;
+    io.v_out = e->v_out, io.lossTile = e->lossTile;
+    return io;
+}
+
+// RawGaussianModel::forward -> gesForward (src/raw_gs_model.cpp:188-367) without autograd: rgb [H,W,3], depth [H,W], alpha [H,W]
+extern "C" int gsb_gs_render(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
+                             const float *base_color_dev, float *rgb_dev, float *depth_dev, float *alpha_dev)
+{
+    if (!e || !c2w || !ref_depth_dev || !base_color_dev || !rgb_dev || !depth_dev || !alpha_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    CamParams cam;
+    make_camera(e, c2w, fx, fy, cx, cy, cam);
+    project_sh_fwd(e->p, e->nDev, e->nUpper, cam, e->recs, e->grads, e->bins, e->tileW, e->tileH, false, e->stream);
+    bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
+    RasterIO io = make_io(e, ref_depth_dev, base_color_dev, nullptr);
+    io.rgb = rgb_dev, io.depth = depth_dev, io.alphas = alpha_dev;
+    raster_fwd(RASTER_RENDER, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// One optimiser iteration of SLAMPipeline::localOptimize (slam/slam_pipeline.cpp:222-254): model.forward + computeLoss (L1) +
+// backward + optimizersStep + optimizersZeroGrad.
+extern "C" int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
+                                 const float *base_color_dev, const float *gt_rgb_dev)
+{
+    if (!e || !c2w || !ref_depth_dev || !base_color_dev || !gt_rgb_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    CamParams cam;
+    make_camera(e, c2w, fx, fy, cx, cy, cam);
+    project_sh_fwd(e->p, e->nDev, e->nUpper, cam, e->recs, e->grads, e->bins, e->tileW, e->tileH, true, e->stream);
+    bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
+    RasterIO io = make_io(e, ref_depth_dev, base_color_dev, gt_rgb_dev);
+    raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    if (e->nUpper > 0)
+        raster_bwd(e->recs, e->bins, e->W, e->H, io, nullptr, e->grads, e->stream);
+    // torch::optim::Adam: step count is per optimiser, identical for the 6 of them
+    e->adamStep++;
+    const double b1 = (double)0.9f, b2 = (double)0.999f; // float betas widened to double (src/raw_gs_model.cpp:662-663)
+    const double bc1 = 1.0 - pow(b1, e->adamStep), bc2 = 1.0 - pow(b2, e->adamStep);
+    AdamStep s;
+    s.a.beta1 = (float)b1, s.a.beta2 = (float)b2;
+    s.a.one_m_beta1 = (float)(1.0 - b1), s.a.one_m_beta2 = (float)(1.0 - b2);
+    s.a.sqrt_bc2 = (float)sqrt(bc2);
+    s.a.eps = 1e-15f;
+    const double lr[6] = {(double)e->cfg.lr_means * e->cfg.scene_scale, e->cfg.lr_scales, e->cfg.lr_quats, e->cfg.lr_dc, e->cfg.lr_rest, e->cfg.lr_opac};
+    for (int i = 0; i < 6; i++)
+        s.step_size[i] = (float)(lr[i] / bc1);
+    bwd_params_adam(e->p, e->m, e->v, e->touched, s, e->nDev, e->nUpper, cam, e->recs, e->grads, e->haveDbg ? &e->dbg : nullptr, e->bins.counters,
+                    e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// loss of the last train step: mean |gt - rgb| (synchronises)
+extern "C" int gsb_gs_loss(gsb_gs_t *e, double *loss)
+{
+    reduce_loss(e->lossTile, e->T, 1.0 / (3.0 * e->W * e->H), e->lossDev, e->stream);
+    GS_CUDA_OK(cudaMemcpyAsync(e->hostLoss, e->lossDev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    *loss = *e->hostLoss;
+    return 0;
+}
+
+// SLAMPipeline::removeRedundantGs (slam/slam_pipeline.cpp:564-586) -> RawGaussianModel::prunePoints. No host round trip: the new
+// count stays on the device, the host keeps the old count as launch bound until the next gsb_gs_count.
+extern "C" int gsb_gs_prune(gsb_gs_t *e, float min_opac, float min_scale, float max_scale)
+{
+    if (e->nUpper <= 0)
+        return 0;
+    prune(e->p, e->tmp, e->nDev, e->nUpper, min_opac, min_scale, max_scale, e->scanTmp, e->bins.counters, e->stream);
+    ParamPtrs t = e->p;
+    e->p = e->tmp;
+    e->tmp = t;
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_enable_grad_dump(gsb_gs_t *e, int on)
+{
+    if (on && !e->dbg.means)
+        if (alloc_params(e, e->dbg, e->cap))
+            return 1;
+    e->haveDbg = on != 0;
+    return 0;
+}
+
+extern "C" int gsb_gs_read(gsb_gs_t *e, int what, void *dst, size_t bytes)
+{
+    const void *src = nullptr;
+    size_t avail = 0;
+    const size_t P = (size_t)e->W * e->H;
+    switch (what)
+    {
+    case GSB_GS_SPLAT_RECORDS: src = e->recs, avail = (size_t)e->cap * sizeof(SplatRec); break;
+    case GSB_GS_SPLAT_GRADS: src = e->grads, avail = (size_t)e->cap * sizeof(SplatGrad); break;
+    case GSB_GS_TILE_OFFSETS: src = e->bins.tileOffsets, avail = (size_t)(e->T + 1) * 4; break;
+    case GSB_GS_FLATTEN_IDS: src = e->bins.flattenSorted, avail = (size_t)e->bins.isectCap * 4; break;
+    case GSB_GS_V_OUT: src = e->v_out, avail = P * 16; break;
+    case GSB_GS_COUNTERS: src = e->bins.counters, avail = CNT_TOTAL * 4; break;
+    case GSB_GS_GRAD_MEANS: src = e->dbg.means, avail = (size_t)e->cap * 12; break;
+    case GSB_GS_GRAD_SCALES: src = e->dbg.scales, avail = (size_t)e->cap * 12; break;
+    case GSB_GS_GRAD_QUATS: src = e->dbg.quats, avail = (size_t)e->cap * 16; break;
+    case GSB_GS_GRAD_DC: src = e->dbg.dc, avail = (size_t)e->cap * 12; break;
+    case GSB_GS_GRAD_REST: src = e->dbg.rest, avail = (size_t)e->cap * 180; break;
+    case GSB_GS_GRAD_OPAC: src = e->dbg.opac, avail = (size_t)e->cap * 4; break;
+    default: return gs_set_error(__FILE__, __LINE__, "bad read id");
+    }
+    if (!src)
+        return gs_set_error(__FILE__, __LINE__, "buffer not allocated (gsb_gs_enable_grad_dump)");
+    if (bytes > avail)
+        return gs_set_error(__FILE__, __LINE__, "read larger than the buffer");
+    GS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}

@@ -390,13 +390,13 @@ __device__ __forceinline__ void project_vjp(const float *scale, const CamParams 
 // A12: one Adam update (torch::optim::Adam semantics, see oracle/gs_oracle.py adam_step); returns new parameter
 struct AdamScalars
 {
-    float beta1, beta2, one_m_beta1, one_m_beta2, inv_sqrt_bc2, eps;
+    float beta1, beta2, one_m_beta1, one_m_beta2, sqrt_bc2, eps;
 };
 __device__ __forceinline__ float adam_update(float p, float g, float &m, float &v, const AdamScalars &a, float step_size)
 {
     m = m * a.beta1 + g * a.one_m_beta1;
     v = v * a.beta2 + g * g * a.one_m_beta2;
-    float denom = sqrtf(v) * a.inv_sqrt_bc2 + a.eps;
+    float denom = sqrtf(v) / a.sqrt_bc2 + a.eps;
     return p - step_size * (m / denom);
 }
 

@@ -1,0 +1,587 @@
+// gsplat-GES path, per-Gaussian side, hand-written for sm_100a.
+// Built with -fmad=false: the forward expressions follow oracle/gs_oracle.py operation by operation so that the integer
+// artefacts (radii, tile rectangles, bins) are bit-identical to the restated reference.
+//
+// What replaces what (reference file:line):
+//   k_project_sh      getRealScales/getRealOpacities (include/raw_gs_param.h:80-82) + fully_fused_projection_fwd_kernel
+//                     (gsplat/rasterizer/fully_fused_projection_fwd.cu:20-194) + clamp_max(radii) (src/raw_gs_model.cpp:241-242)
+//                     + viewDirs / cat(featuresDc, featuresRest) / compute_sh_fwd_kernel / clamp_min(c+0.5, 0)
+//                     (src/raw_gs_model.cpp:253-257, gsplat/rasterizer/compute_sh_fwd.cu:12-38) + the first pass of
+//                     isect_tiles_no_depth (isect_tiles_no_depth.cu:57-90): one pass over the parameters, no intermediates
+//                     in HBM except the 48-byte splat record.
+//   k_scan_tiles / k_scatter_tiles / k_sort_tiles
+//                     cumsum + second pass of isect_tiles_no_depth + cub::DeviceRadixSort + isect_offset_encode_no_depth
+//                     (isect_tiles_no_depth.cu:132-371, 373-461).  Counting sort by tile with a per-tile ordering pass gives the
+//                     same (tile, ascending Gaussian id) order as the reference's stable radix sort, with every size kept on
+//                     the device (the reference reads n_isects / n_groups back with .item() twice per iteration).
+//   k_bwd_params_adam compute_sh_bwd_kernel (compute_sh_bwd.cu:14-54) + fully_fused_projection_bwd_kernel
+//                     (fully_fused_projection_bwd.cu:21-265) + exp/sigmoid backward + 6 x torch::optim::Adam::step
+//                     (src/raw_gs_model.cpp:654-705) in one pass over parameters and optimiser state.
+#include "common.cuh"
+#include "gs.h"
+
+namespace gs
+{
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// tile rectangle of a splat: isect_tiles_no_depth.cu:70-80 (the float -> uint32 casts saturate on the GPU)
+__device__ __forceinline__ void tile_rect(float m2x, float m2y, int radius, int tileW, int tileH, int &x0, int &y0, int &x1, int &y1)
+{
+    float ts = (float)TILE;
+    float tr = (float)radius / ts;
+    float tx = m2x / ts, ty = m2y / ts;
+    x0 = (int)min((unsigned)floorf(tx - tr), (unsigned)tileW);
+    y0 = (int)min((unsigned)floorf(ty - tr), (unsigned)tileH);
+    x1 = (int)min((unsigned)ceilf(tx + tr), (unsigned)tileW);
+    y1 = (int)min((unsigned)ceilf(ty + tr), (unsigned)tileH);
+}
+
+__device__ __forceinline__ int bwd_groups(int radius)
+{
+    float r = (float)radius;
+    return (int)((4.0f * r * r + 32.0f - 1.0f) / 32.0f); // groups_per_gauss, evaluated in float like the reference (:87)
+}
+
+__device__ __forceinline__ void load_coeffs(const ParamPtrs &p, int g, float *cl /* [16][3] */)
+{
+    cl[0] = p.dc[g * 3 + 0], cl[1] = p.dc[g * 3 + 1], cl[2] = p.dc[g * 3 + 2];
+    const float *r = p.rest + (size_t)g * 45;
+#pragma unroll
+    for (int i = 0; i < 45; i++)
+        cl[3 + i] = r[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__restrict__ nDev, CamParams cam, SplatRec *__restrict__ recs,
+                                                     SplatGrad *__restrict__ grads, int *tileCount, int tileW, int tileH, int2 *items,
+                                                     int itemCap, int *counters, int forBackward)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool inRange = g < *nDev;
+    Proj o;
+    o.radius = 0;
+    float mean[3];
+    if (inRange)
+    {
+        mean[0] = p.means[g * 3 + 0], mean[1] = p.means[g * 3 + 1], mean[2] = p.means[g * 3 + 2];
+        float scale[3] = {expf(p.scales[g * 3 + 0]), expf(p.scales[g * 3 + 1]), expf(p.scales[g * 3 + 2])};
+        float4 q4 = reinterpret_cast<const float4 *>(p.quats)[g];
+        float quat[4] = {q4.x, q4.y, q4.z, q4.w};
+        o = project_one(mean, quat, scale, cam, nullptr);
+    }
+    const bool vis = o.radius > 0;
+    int nItems = 0;
+    int bits = 0;
+    float col[3] = {0.f, 0.f, 0.f};
+    float opac = 0.f;
+    if (vis)
+    {
+        opac = 1.0f / (1.0f + expf(-p.opac[g]));
+        // SH colour (degree 3), dirs = means - camT, colour = max(SH + 0.5, 0)
+        float dir[3] = {mean[0] - cam.cam_pos[0], mean[1] - cam.cam_pos[1], mean[2] - cam.cam_pos[2]};
+        ShBasis sb;
+        sh_basis(dir, sb);
+        float cl[48];
+        load_coeffs(p, g, cl);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+        {
+            float raw = sh_eval_channel(sb, cl + c, 3) + 0.5f;
+            if (raw >= 0.f)
+                bits |= 1 << c;
+            col[c] = fmaxf(raw, 0.f);
+        }
+        int x0, y0, x1, y1;
+        tile_rect(o.m2x, o.m2y, o.radius, tileW, tileH, x0, y0, x1, y1);
+        for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++)
+                atomicAdd(&tileCount[ty * tileW + tx], 1);
+        if (forBackward)
+        {
+            int groups = bwd_groups(o.radius);
+            nItems = (groups + BWD_GROUPS_PER_ITEM - 1) / BWD_GROUPS_PER_ITEM;
+            if (nItems > 1)
+            {
+                bits |= 256; // several warps accumulate into this splat's gradient with atomics: start from zero
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                grads[g].g0 = z, grads[g].g1 = z, grads[g].g2 = z;
+            }
+        }
+    }
+    // warp-aggregated reservation of backward work items and of the visible count (one atomic per warp)
+    const unsigned full = 0xffffffffu;
+    unsigned vm = __ballot_sync(full, vis);
+    if (vm == 0)
+    {
+        if (inRange)
+            recs[g].q0 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        return;
+    }
+    int incl = nItems;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        int n = __shfl_up_sync(full, incl, d);
+        if (lane >= d)
+            incl += n;
+    }
+    int total = __shfl_sync(full, incl, 31);
+    int base = 0;
+    if (lane == 31)
+    {
+        atomicAdd(&counters[CNT_VISIBLE], __popc(vm));
+        if (total > 0)
+            base = atomicAdd(&counters[CNT_ITEMS], total);
+    }
+    base = __shfl_sync(full, base, 31) + incl - nItems;
+    if (nItems > 0)
+    {
+        if (base + nItems <= itemCap)
+        {
+            for (int i = 0; i < nItems; i++)
+                items[base + i] = make_int2(g, i);
+        }
+        else
+            atomicOr(&counters[CNT_OVERFLOW], 2);
+    }
+    if (!inRange)
+        return;
+    if (!vis)
+    {
+        recs[g].q0 = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        return;
+    }
+    SplatRec r;
+    r.q0 = make_float4(o.m2x, o.m2y, opac, __int_as_float(o.radius));
+    r.q1 = make_float4(o.ca, o.cb, o.cc, o.depth);
+    r.q2 = make_float4(col[0], col[1], col[2], __int_as_float(bits));
+    recs[g] = r;
+}
+
+// exclusive scan of the per-tile counts (T + 1 <= a few 10^4 entries) by one CTA; also re-arms the per-iteration counters
+__global__ void __launch_bounds__(1024) k_scan_tiles(int *tileCount, int *tileOffsets, int *tileCursor, int T, int isectCap, int *counters)
+{
+    __shared__ int warpSums[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0)
+        carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024)
+    {
+        int i = base + tid;
+        int v = (i < T) ? tileCount[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d)
+                incl += n;
+        }
+        if (lane == 31)
+            warpSums[wid] = incl;
+        __syncthreads();
+        if (wid == 0)
+        {
+            int w = warpSums[lane];
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                int n = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d)
+                    wi += n;
+            }
+            warpSums[lane] = wi - w; // exclusive
+        }
+        __syncthreads();
+        int excl = carry + warpSums[wid] + incl - v;
+        if (i < T)
+        {
+            tileOffsets[i] = min(excl, isectCap);
+            tileCursor[i] = 0;
+            tileCount[i] = 0;
+        }
+        __syncthreads();
+        if (tid == 1023)
+            carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0)
+    {
+        int total = carry;
+        if (total > isectCap)
+        {
+            atomicOr(&counters[CNT_OVERFLOW], 1);
+            total = isectCap;
+        }
+        tileOffsets[T] = total;
+        counters[CNT_ISECTS] = total;
+        counters[CNT_VISIBLE_LAST] = counters[CNT_VISIBLE];
+        counters[CNT_VISIBLE] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_tiles(const SplatRec *__restrict__ recs, const int *__restrict__ nDev,
+                                                        const int *__restrict__ tileOffsets, int *tileCursor, int *flatten, int isectCap, int tileW,
+                                                        int tileH)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= *nDev)
+        return;
+    float4 q0 = __ldg(&recs[g].q0);
+    int radius = __float_as_int(q0.w);
+    if (radius <= 0)
+        return;
+    int x0, y0, x1, y1;
+    tile_rect(q0.x, q0.y, radius, tileW, tileH, x0, y0, x1, y1);
+    for (int ty = y0; ty < y1; ty++)
+        for (int tx = x0; tx < x1; tx++)
+        {
+            int t = ty * tileW + tx;
+            int pos = tileOffsets[t] + atomicAdd(&tileCursor[t], 1);
+            if (pos < isectCap)
+                flatten[pos] = g;
+        }
+}
+
+// per tile: order the scattered ids ascending (= the order of the reference's stable sort by tile id)
+constexpr int SORT_SMEM = 4096;
+__global__ void __launch_bounds__(256) k_sort_tiles(const int *__restrict__ tileOffsets, const int *__restrict__ flatten, int *flattenSorted)
+{
+    __shared__ int s[SORT_SMEM];
+    const int t = blockIdx.x;
+    const int start = tileOffsets[t], L = tileOffsets[t + 1] - start;
+    if (L <= 0)
+        return;
+    const int tid = threadIdx.x;
+    if (L == 1)
+    {
+        if (tid == 0)
+            flattenSorted[start] = flatten[start];
+        return;
+    }
+    if (L <= SORT_SMEM)
+    {
+        int n = 2;
+        while (n < L)
+            n <<= 1;
+        for (int i = tid; i < n; i += 256)
+            s[i] = (i < L) ? flatten[start + i] : 0x7fffffff;
+        __syncthreads();
+        for (int k = 2; k <= n; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1)
+            {
+                for (int i = tid; i < n; i += 256)
+                {
+                    int ixj = i ^ j;
+                    if (ixj > i)
+                    {
+                        int a = s[i], b = s[ixj];
+                        bool asc = (i & k) == 0;
+                        if ((a > b) == asc)
+                            s[i] = b, s[ixj] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = tid; i < L; i += 256)
+            flattenSorted[start + i] = s[i];
+    }
+    else
+    {
+        // very long list (> SORT_SMEM splats on one 16x16 tile): rank sort straight from global memory; ids are unique
+        for (int i = tid; i < L; i += 256)
+        {
+            int a = flatten[start + i];
+            int rank = 0;
+            for (int j = 0; j < L; j++)
+                rank += (flatten[start + j] < a);
+            flattenSorted[start + rank] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_one(float *p, float *m, float *v, size_t idx, float g, bool hadState, const AdamScalars &a, float stepSize)
+{
+    float mo = hadState ? m[idx] : 0.f;
+    float vo = hadState ? v[idx] : 0.f;
+    float pn = adam_update(p[idx], g, mo, vo, a, stepSize);
+    p[idx] = pn, m[idx] = mo, v[idx] = vo;
+}
+
+__global__ void __launch_bounds__(128) k_bwd_params_adam(ParamPtrs p, ParamPtrs m, ParamPtrs v, unsigned char *touched, AdamStep step,
+                                                          const int *__restrict__ nDev, CamParams cam, const SplatRec *__restrict__ recs,
+                                                          const SplatGrad *__restrict__ grads, ParamPtrs dbg, int haveDbg, int *counters)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0)
+    {
+        counters[CNT_ITEMS] = 0; // re-arm for the next projection
+    }
+    if (g >= *nDev)
+        return;
+    float4 q0 = recs[g].q0;
+    const int radius = __float_as_int(q0.w);
+    const bool vis = radius > 0;
+    const bool had = touched[g] != 0;
+    if (!vis && !had && !haveDbg)
+        return;
+    float gm[3] = {0.f, 0.f, 0.f}, gsc[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gdc[3] = {0.f, 0.f, 0.f}, gop = 0.f;
+    float basis[16], vcol[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        basis[k] = 0.f;
+    if (vis)
+    {
+        float4 q1 = recs[g].q1, q2 = recs[g].q2;
+        SplatGrad sg = grads[g];
+        int bits = __float_as_int(q2.w);
+        vcol[0] = (bits & 1) ? sg.g2.x : 0.f;
+        vcol[1] = (bits & 2) ? sg.g2.y : 0.f;
+        vcol[2] = (bits & 4) ? sg.g2.z : 0.f;
+        float mean[3] = {p.means[g * 3 + 0], p.means[g * 3 + 1], p.means[g * 3 + 2]};
+        float scale[3] = {expf(p.scales[g * 3 + 0]), expf(p.scales[g * 3 + 1]), expf(p.scales[g * 3 + 2])};
+        float4 q4 = reinterpret_cast<const float4 *>(p.quats)[g];
+        float quat[4] = {q4.x, q4.y, q4.z, q4.w};
+        ProjIntermediates keep;
+        project_one(mean, quat, scale, cam, &keep);
+        float dir[3] = {mean[0] - cam.cam_pos[0], mean[1] - cam.cam_pos[1], mean[2] - cam.cam_pos[2]};
+        ShBasis sb;
+        sh_basis(dir, sb);
+        float cl[48];
+        load_coeffs(p, g, cl);
+        float vdir[3];
+        sh_vjp(sb, cl, 3, vcol, basis, vdir);
+        float vmean[3], vquat[4], vscale[3];
+        project_vjp(scale, cam, keep, q1.x, q1.y, q1.z, sg.g0.x, sg.g0.y, sg.g0.w, sg.g1.x, sg.g1.y, sg.g1.z, vmean, vquat, vscale);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            gm[i] = vmean[i] + vdir[i];
+            gsc[i] = vscale[i] * scale[i];
+            gdc[i] = basis[0] * vcol[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            gq[i] = vquat[i];
+        float o = q0.z;
+        gop = sg.g0.z * o * (1.0f - o);
+    }
+    if (haveDbg)
+    {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            dbg.means[g * 3 + i] = gm[i], dbg.scales[g * 3 + i] = gsc[i], dbg.dc[g * 3 + i] = gdc[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            dbg.quats[g * 4 + i] = gq[i];
+        dbg.opac[g] = gop;
+        for (int e = 0; e < 45; e++)
+            dbg.rest[(size_t)g * 45 + e] = basis[e / 3 + 1] * vcol[e % 3];
+        if (!vis && !had)
+            return;
+    }
+    // Adam: a Gaussian that never received a gradient in this optimiser cycle has m = v = 0 and a zero update, so it is
+    // skipped exactly; its state is materialised on first touch.
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        adam_one(p.means, m.means, v.means, (size_t)g * 3 + i, gm[i], had, step.a, step.step_size[0]);
+        adam_one(p.scales, m.scales, v.scales, (size_t)g * 3 + i, gsc[i], had, step.a, step.step_size[1]);
+        adam_one(p.dc, m.dc, v.dc, (size_t)g * 3 + i, gdc[i], had, step.a, step.step_size[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        adam_one(p.quats, m.quats, v.quats, (size_t)g * 4 + i, gq[i], had, step.a, step.step_size[2]);
+    adam_one(p.opac, m.opac, v.opac, (size_t)g, gop, had, step.a, step.step_size[5]);
+#pragma unroll 3
+    for (int e = 0; e < 45; e++)
+    {
+        int k = e / 3 + 1, c = e - (e / 3) * 3;
+        float ge = vis ? basis[k] * vcol[c] : 0.f;
+        adam_one(p.rest, m.rest, v.rest, (size_t)g * 45 + e, ge, had, step.a, step.step_size[4]);
+    }
+    touched[g] = 1;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_loss(const float *__restrict__ lossTile, int T, double scale, double *out)
+{
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < T; i += 256)
+        acc += (double)lossTile[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1)
+    {
+        if (threadIdx.x < d)
+            s[threadIdx.x] += s[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        *out = s[0] * scale;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// removeRedundantGs (slam/slam_pipeline.cpp:564-586) + prunePoints: keep = !(max scale < minScale | max scale > maxScale | opacity < minOpac)
+__device__ __forceinline__ bool prune_keep(const ParamPtrs &p, int g, float minOpac, float minScale, float maxScale)
+{
+    float s = fmaxf(fmaxf(expf(p.scales[g * 3 + 0]), expf(p.scales[g * 3 + 1])), expf(p.scales[g * 3 + 2]));
+    float o = 1.0f / (1.0f + expf(-p.opac[g]));
+    return !((s < minScale) || (s > maxScale) || (o < minOpac));
+}
+
+__device__ __forceinline__ int block_excl_scan_1024(int v, int *warpSums, int &total)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += n;
+    }
+    if (lane == 31)
+        warpSums[wid] = incl;
+    __syncthreads();
+    if (wid == 0)
+    {
+        int w = warpSums[lane];
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            int n = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d)
+                wi += n;
+        }
+        warpSums[lane] = wi - w;
+        if (lane == 31)
+            warpSums[32] = wi;
+    }
+    __syncthreads();
+    total = warpSums[32];
+    int r = warpSums[wid] + incl - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(1024) k_prune_count(ParamPtrs p, const int *__restrict__ nDev, float minOpac, float minScale, float maxScale,
+                                                       int *chunkCnt)
+{
+    __shared__ int ws[33];
+    int g = blockIdx.x * 1024 + threadIdx.x;
+    int keep = (g < *nDev) ? (int)prune_keep(p, g, minOpac, minScale, maxScale) : 0;
+    int total;
+    block_excl_scan_1024(keep, ws, total);
+    if (threadIdx.x == 0)
+        chunkCnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_prune_scan(int *chunkCnt, int nChunks, int *nDev, int *counters)
+{
+    __shared__ int ws[33];
+    __shared__ int carry;
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nChunks; base += 1024)
+    {
+        int i = base + threadIdx.x;
+        int v = i < nChunks ? chunkCnt[i] : 0;
+        int total;
+        int ex = block_excl_scan_1024(v, ws, total);
+        if (i < nChunks)
+            chunkCnt[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        counters[CNT_SCRATCH + 1] = *nDev; // old count, read by the scatter pass
+        counters[CNT_SCRATCH] = carry;
+        *nDev = carry;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_prune_scatter(ParamPtrs p, ParamPtrs q, const int *__restrict__ counters, float minOpac, float minScale,
+                                                         float maxScale, const int *__restrict__ chunkOff)
+{
+    __shared__ int ws[33];
+    int g = blockIdx.x * 1024 + threadIdx.x;
+    int nOld = counters[CNT_SCRATCH + 1];
+    int keep = (g < nOld) ? (int)prune_keep(p, g, minOpac, minScale, maxScale) : 0;
+    int total;
+    int ex = block_excl_scan_1024(keep, ws, total);
+    if (!keep)
+        return;
+    int d = chunkOff[blockIdx.x] + ex;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        q.means[d * 3 + i] = p.means[g * 3 + i], q.scales[d * 3 + i] = p.scales[g * 3 + i], q.dc[d * 3 + i] = p.dc[g * 3 + i];
+    reinterpret_cast<float4 *>(q.quats)[d] = reinterpret_cast<const float4 *>(p.quats)[g];
+    q.opac[d] = p.opac[g];
+    for (int e = 0; e < 45; e++)
+        q.rest[(size_t)d * 45 + e] = p.rest[(size_t)g * 45 + e];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch wrappers
+void project_sh_fwd(const ParamPtrs &p, const int *nDev, int nUpper, const CamParams &cam, SplatRec *recs, SplatGrad *grads, const Bins &bins,
+                    int tileW, int tileH, bool forBackward, cudaStream_t st)
+{
+    if (nUpper <= 0)
+        return;
+    GS_COUNT_LAUNCHES(1);
+    k_project_sh<<<cdiv(nUpper, 128), 128, 0, st>>>(p, nDev, cam, recs, grads, bins.tileCount, tileW, tileH, bins.items, bins.itemCap,
+                                                    bins.counters, forBackward ? 1 : 0);
+}
+
+void bin_tiles(const SplatRec *recs, const int *nDev, int nUpper, const Bins &bins, int tileW, int tileH, cudaStream_t st)
+{
+    const int T = tileW * tileH;
+    GS_COUNT_LAUNCHES(3);
+    k_scan_tiles<<<1, 1024, 0, st>>>(bins.tileCount, bins.tileOffsets, bins.tileCursor, T, bins.isectCap, bins.counters);
+    if (nUpper > 0)
+        k_scatter_tiles<<<cdiv(nUpper, 256), 256, 0, st>>>(recs, nDev, bins.tileOffsets, bins.tileCursor, bins.flatten, bins.isectCap, tileW, tileH);
+    k_sort_tiles<<<T, 256, 0, st>>>(bins.tileOffsets, bins.flatten, bins.flattenSorted);
+}
+
+void bwd_params_adam(const ParamPtrs &p, const ParamPtrs &m, const ParamPtrs &v, unsigned char *touched, const AdamStep &step, const int *nDev,
+                     int nUpper, const CamParams &cam, const SplatRec *recs, const SplatGrad *grads, const ParamPtrs *dbg, int *counters,
+                     cudaStream_t st)
+{
+    if (nUpper <= 0)
+        return;
+    GS_COUNT_LAUNCHES(1);
+    ParamPtrs d = dbg ? *dbg : p;
+    k_bwd_params_adam<<<cdiv(nUpper, 128), 128, 0, st>>>(p, m, v, touched, step, nDev, cam, recs, grads, d, dbg ? 1 : 0, counters);
+}
+
+void reduce_loss(const float *lossTile, int T, double scale, double *out, cudaStream_t st)
+{
+    GS_COUNT_LAUNCHES(1);
+    k_reduce_loss<<<1, 256, 0, st>>>(lossTile, T, scale, out);
+}
+
+void prune(const ParamPtrs &p, const ParamPtrs &tmp, int *nDev, int nUpper, float minOpac, float minScale, float maxScale, int *scanTmp,
+           int *counters, cudaStream_t st)
+{
+    if (nUpper <= 0)
+        return;
+    int nChunks = cdiv(nUpper, 1024);
+    GS_COUNT_LAUNCHES(3);
+    k_prune_count<<<nChunks, 1024, 0, st>>>(p, nDev, minOpac, minScale, maxScale, scanTmp);
+    k_prune_scan<<<1, 1024, 0, st>>>(scanTmp, nChunks, nDev, counters);
+    k_prune_scatter<<<nChunks, 1024, 0, st>>>(p, tmp, counters, minOpac, minScale, maxScale, scanTmp);
+}
+
+} // namespace gs

@@ -1,0 +1,276 @@
+// gsplat-GES rasteriser, forward and Gaussian-parallel backward, hand-written for sm_100a.
+//
+//   k_raster_fwd   rasterize_to_pixels_fwd_ges_kernel (gsplat/rasterizer/rasterize_to_pixels_fwd_ges.cu:18-221) fused with the
+//                  ref-depth clamp (src/raw_gs_model.cpp:207), the weighted-average composite with the TSDF render
+//                  (src/raw_gs_model.cpp:317-326), the L1 loss (src/raw_gs_model.cpp:369-417, src/tensor_math.cpp:41-44) and
+//                  the head of the backward pass (autograd of the composite and of mean|gt - rgb|): one pass over the image
+//                  instead of ~25 elementwise launches.  Splat records (48 B) are staged per batch in shared memory, colours
+//                  included (the reference gathers colours from global memory per pixel-splat hit).
+//   k_raster_bwd   temp_bwd_kernel (gsplat/rasterizer/rasterize_to_pixels_bwd_ges_new_parallel.cu:18-201): same support (the
+//                  2r x 2r pixel box of each splat, NOT the forward's tile footprint), same validity tests, same per-lane
+//                  pixel assignment (32 consecutive box-linear ids per step).  A warp owns up to 64 consecutive groups of one
+//                  splat and keeps the 10 gradient sums in registers across them, so there is one shuffle reduction and one
+//                  store (or 10 atomics for splats wider than 45 px) per work item instead of per 32 pixels, and no idle
+//                  warps (the reference launches 32x more warps than it uses).
+#include "common.cuh"
+#include "gs.h"
+
+namespace gs
+{
+
+constexpr int RB = 256; // splats per staged batch = threads per tile CTA
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__ recs, const int *__restrict__ tileOffsets,
+                                                     const int *__restrict__ flattenSorted, int W, int H, int tileW, RasterIO io, float invCount)
+{
+    __shared__ float4 s0[RB], s1[RB], s2[RB];
+    __shared__ float warpLoss[8];
+    const int tile = blockIdx.x;
+    const int tyi = tile / tileW, txi = tile - tyi * tileW;
+    const int tid = threadIdx.x;
+    const int i = tyi * TILE + (tid >> 4), j = txi * TILE + (tid & 15);
+    const bool inside = (i < H) && (j < W);
+    const int pix = i * W + j;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int start = tileOffsets[tile], end = tileOffsets[tile + 1];
+
+    float rdRaw = inside ? __ldg(&io.refDepth[pix]) : 0.f;
+    float rd = (io.clampRef && rdRaw < 0.01f) ? 1000.0f : rdRaw;
+    const float cut = rd + io.deltaDepth;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, w = 0.f;
+
+    for (int b = start; b < end; b += RB)
+    {
+        __syncthreads();
+        int idx = b + tid;
+        if (idx < end)
+        {
+            const SplatRec *r = recs + __ldg(&flattenSorted[idx]);
+            s0[tid] = __ldg(&r->q0);
+            s1[tid] = __ldg(&r->q1);
+            s2[tid] = __ldg(&r->q2);
+        }
+        __syncthreads();
+        const int n = min(RB, end - b);
+        if (inside)
+        {
+            for (int t = 0; t < n; t++)
+            {
+                const float4 c = s1[t];
+                if (c.w > cut)
+                    continue;
+                const float4 xyo = s0[t];
+                const float dx = xyo.x - px, dy = xyo.y - py;
+                const float sigma = 0.5f * (c.x * dx * dx + c.z * dy * dy) + c.y * dx * dy;
+                const float alpha = fminf(0.999f, xyo.z * __expf(-sigma));
+                if (sigma < 0.f || alpha < 1.f / 255.f)
+                    continue;
+                const float4 col = s2[t];
+                a0 += col.x * alpha;
+                a1 += col.y * alpha;
+                a2 += col.z * alpha;
+                a3 += c.w * alpha;
+                w += alpha;
+            }
+        }
+    }
+
+    if (MODE == RASTER_RAW)
+    {
+        if (inside)
+        {
+            reinterpret_cast<float4 *>(io.render4)[pix] = make_float4(a0, a1, a2, a3);
+            io.alphas[pix] = w;
+        }
+        return;
+    }
+    // composite with the TSDF render: rgb = (acc + base) / (w + 1), depth = (acc_d + D*[D>0]) / (w + [D>0])
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    float w1 = w + 1.0f;
+    if (inside)
+    {
+        const float *bc = io.baseColor + (size_t)pix * 3;
+        r0 = (a0 + __ldg(bc + 0) * 1.0f) / w1;
+        r1 = (a1 + __ldg(bc + 1) * 1.0f) / w1;
+        r2 = (a2 + __ldg(bc + 2) * 1.0f) / w1;
+    }
+    if (MODE == RASTER_RENDER)
+    {
+        if (inside)
+        {
+            float bw = rdRaw > 0.f ? 1.0f : 0.0f;
+            float *o = io.rgb + (size_t)pix * 3;
+            o[0] = r0, o[1] = r1, o[2] = r2;
+            io.depth[pix] = (a3 + rdRaw * bw) / (w + bw);
+            io.alphas[pix] = w;
+        }
+        return;
+    }
+    // TRAIN: loss = mean |gt - rgb| over 3P elements; v_rgb = sign(rgb - gt) / (3P);
+    //        v_render_c = v_rgb_c / (w + 1); v_render_alpha = -sum_c v_rgb_c * rgb_c / (w + 1)
+    float lsum = 0.f;
+    if (inside)
+    {
+        const float *gt = io.gt + (size_t)pix * 3;
+        float d0 = r0 - __ldg(gt + 0), d1 = r1 - __ldg(gt + 1), d2 = r2 - __ldg(gt + 2);
+        lsum = fabsf(d0) + fabsf(d1) + fabsf(d2);
+        float v0 = d0 > 0.f ? invCount : (d0 < 0.f ? -invCount : 0.f);
+        float v1 = d1 > 0.f ? invCount : (d1 < 0.f ? -invCount : 0.f);
+        float v2 = d2 > 0.f ? invCount : (d2 < 0.f ? -invCount : 0.f);
+        float va = -(v0 * r0 + v1 * r1 + v2 * r2) / w1;
+        io.v_out[pix] = make_float4(v0 / w1, v1 / w1, v2 / w1, va);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
+    if ((tid & 31) == 0)
+        warpLoss[tid >> 5] = lsum;
+    __syncthreads();
+    if (tid == 0)
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            s += warpLoss[k];
+        io.lossTile[tile] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__ recs, const int2 *__restrict__ items,
+                                                     const int *__restrict__ counters, int itemCap, int W, int H,
+                                                     const float *__restrict__ refDepth, int clampRef, float deltaDepth,
+                                                     const float4 *__restrict__ v_out, const float *__restrict__ v_depthImg,
+                                                     SplatGrad *__restrict__ grads)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int nWarps = gridDim.x * warpsPerBlock;
+    const int nItems = min(counters[CNT_ITEMS], itemCap);
+    for (int it = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); it < nItems; it += nWarps)
+    {
+        const int2 item = __ldg(&items[it]);
+        const int g = item.x;
+        const float4 q0 = __ldg(&recs[g].q0), q1 = __ldg(&recs[g].q1), q2 = __ldg(&recs[g].q2);
+        const int radius = __float_as_int(q0.w);
+        const float opac = q0.z;
+        const int x_min = (int)q0.x - radius, y_min = (int)q0.y - radius, y_max = (int)q0.y + radius;
+        const int bw = 2 * radius;
+        const float inv_bw = 1.0f / (float)bw;
+        const float rr = (float)radius;
+        const int groups = (int)((4.0f * rr * rr + 32.0f - 1.0f) / 32.0f);
+        const int g0 = item.y * BWD_GROUPS_PER_ITEM;
+        const int g1 = min(g0 + BWD_GROUPS_PER_ITEM, groups);
+        float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, vca = 0.f, vcb = 0.f, vcc = 0.f, vx = 0.f, vy = 0.f, vo = 0.f;
+        for (int grp = g0; grp < g1; grp++)
+        {
+            const int id = grp * 32 + lane;
+            const int row = (int)(((float)id + 0.5f) * inv_bw); // exact for id < 2^16, bw <= 200
+            const int col = id - row * bw;
+            const int j = x_min + 1 + col, i = y_min + 1 + row;
+            if (i < 0 || j < 0 || i >= H || j >= W || i > y_max)
+                continue;
+            const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+            const float dx = q0.x - px, dy = q0.y - py;
+            const float sigma = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+            const float vis = __expf(-sigma);
+            const float alpha = fminf(0.999f, opac * vis);
+            if (sigma < 0.f || alpha < 1.f / 255.f)
+                continue;
+            const int pix = i * W + j;
+            float rd = __ldg(&refDepth[pix]);
+            if (clampRef && rd < 0.01f)
+                rd = 1000.0f;
+            if (q1.w > rd + deltaDepth)
+                continue;
+            const float4 vo4 = __ldg(&v_out[pix]);
+            const float vdp = v_depthImg ? __ldg(&v_depthImg[pix]) : 0.f;
+            vr += alpha * vo4.x;
+            vg += alpha * vo4.y;
+            vb += alpha * vo4.z;
+            vd += alpha * vdp;
+            float v_alpha = q2.x * vo4.x + q2.y * vo4.y + q2.z * vo4.z + q1.w * vdp + vo4.w;
+            if (opac * vis <= 0.999f)
+            {
+                const float v_sigma = -opac * vis * v_alpha;
+                vca += 0.5f * v_sigma * dx * dx;
+                vcb += v_sigma * dx * dy;
+                vcc += 0.5f * v_sigma * dy * dy;
+                vx += v_sigma * (q1.x * dx + q1.y * dy);
+                vy += v_sigma * (q1.y * dx + q1.z * dy);
+                vo += vis * v_alpha;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+        {
+            vr += __shfl_xor_sync(0xffffffffu, vr, d);
+            vg += __shfl_xor_sync(0xffffffffu, vg, d);
+            vb += __shfl_xor_sync(0xffffffffu, vb, d);
+            vd += __shfl_xor_sync(0xffffffffu, vd, d);
+            vca += __shfl_xor_sync(0xffffffffu, vca, d);
+            vcb += __shfl_xor_sync(0xffffffffu, vcb, d);
+            vcc += __shfl_xor_sync(0xffffffffu, vcc, d);
+            vx += __shfl_xor_sync(0xffffffffu, vx, d);
+            vy += __shfl_xor_sync(0xffffffffu, vy, d);
+            vo += __shfl_xor_sync(0xffffffffu, vo, d);
+        }
+        if (lane == 0)
+        {
+            SplatGrad *o = grads + g;
+            if (__float_as_int(q2.w) & 256)
+            {
+                float *f = reinterpret_cast<float *>(o);
+                atomicAdd(f + 0, vx), atomicAdd(f + 1, vy), atomicAdd(f + 2, vo), atomicAdd(f + 3, vd);
+                atomicAdd(f + 4, vca), atomicAdd(f + 5, vcb), atomicAdd(f + 6, vcc);
+                atomicAdd(f + 8, vr), atomicAdd(f + 9, vg), atomicAdd(f + 10, vb);
+            }
+            else
+            {
+                o->g0 = make_float4(vx, vy, vo, vd);
+                o->g1 = make_float4(vca, vcb, vcc, 0.f);
+                o->g2 = make_float4(vr, vg, vb, 0.f);
+            }
+        }
+    }
+}
+
+__global__ void k_pack_v_out(int P, const float *__restrict__ v_render4, const float *__restrict__ v_alphas, float4 *v_out, float *v_depth)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P)
+        return;
+    float4 r = reinterpret_cast<const float4 *>(v_render4)[i];
+    v_out[i] = make_float4(r.x, r.y, r.z, v_alphas[i]);
+    v_depth[i] = r.w;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st)
+{
+    const int T = tileW * tileH;
+    const float invCount = 1.0f / (float)((size_t)3 * W * H);
+    GS_COUNT_LAUNCHES(1);
+    if (mode == RASTER_RAW)
+        k_raster_fwd<RASTER_RAW><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount);
+    else if (mode == RASTER_RENDER)
+        k_raster_fwd<RASTER_RENDER><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount);
+    else
+        k_raster_fwd<RASTER_TRAIN><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount);
+}
+
+void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth, SplatGrad *grads, cudaStream_t st)
+{
+    GS_COUNT_LAUNCHES(1);
+    k_raster_bwd<<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, H, io.refDepth, io.clampRef, io.deltaDepth, io.v_out,
+                                          v_depth, grads);
+}
+
+void pack_v_out(int P, const float *v_render4, const float *v_alphas, float4 *v_out, float *v_depth, cudaStream_t st)
+{
+    GS_COUNT_LAUNCHES(1);
+    k_pack_v_out<<<(P + 255) / 256, 256, 0, st>>>(P, v_render4, v_alphas, v_out, v_depth);
+}
+
+} // namespace gs

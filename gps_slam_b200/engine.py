@@ -31,6 +31,18 @@ class TsdfConfig(C.Structure):
                 ("integrate_variant", C.c_int)]
 
 
+class GsConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("capacity", C.c_int), ("isect_capacity", C.c_int), ("item_capacity", C.c_int),
+                ("max_gs_radii", C.c_int), ("delta_depth", C.c_float),
+                ("eps2d", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float), ("radius_clip", C.c_float),
+                ("lr_means", C.c_float), ("lr_scales", C.c_float), ("lr_quats", C.c_float), ("lr_dc", C.c_float), ("lr_rest", C.c_float),
+                ("lr_opac", C.c_float), ("scene_scale", C.c_float), ("device", C.c_int)]
+
+
+(GS_SPLAT_RECORDS, GS_SPLAT_GRADS, GS_TILE_OFFSETS, GS_FLATTEN_IDS, GS_V_OUT, GS_COUNTERS, GS_GRAD_MEANS, GS_GRAD_SCALES, GS_GRAD_QUATS,
+ GS_GRAD_DC, GS_GRAD_REST, GS_GRAD_OPAC) = range(12)
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -73,6 +85,27 @@ def load_library():
     L.gsb_tsdf_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.gsb_tsdf_counter.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.gsb_tsdf_run_stage.argtypes = [C.c_void_p, C.c_int]
+    # ---- section A: Gaussian model
+    vp, fl = C.c_void_p, C.c_float
+    L.gsb_gs_default_config.argtypes = [C.POINTER(GsConfig)]
+    L.gsb_gs_create.argtypes = [C.POINTER(GsConfig), C.POINTER(vp)]
+    L.gsb_gs_destroy.argtypes = [vp]
+    L.gsb_gs_destroy.restype = None
+    L.gsb_gs_set_stream.argtypes = [vp, vp]
+    L.gsb_gs_sync.argtypes = [vp]
+    L.gsb_gs_set_params.argtypes = [vp, C.c_int] + [vp] * 6
+    L.gsb_gs_append.argtypes = [vp, C.c_int] + [vp] * 6
+    L.gsb_gs_get_params.argtypes = [vp, C.c_int] + [vp] * 6
+    L.gsb_gs_count.argtypes = [vp, C.POINTER(C.c_int)]
+    L.gsb_gs_count_upper.argtypes = [vp]
+    L.gsb_gs_init_optimizers.argtypes = [vp]
+    L.gsb_gs_set_learning_rates.argtypes = [vp] + [fl] * 6
+    L.gsb_gs_render.argtypes = [vp, vp, fl, fl, fl, fl, vp, vp, vp, vp, vp]
+    L.gsb_gs_train_step.argtypes = [vp, vp, fl, fl, fl, fl, vp, vp, vp]
+    L.gsb_gs_loss.argtypes = [vp, C.POINTER(C.c_double)]
+    L.gsb_gs_prune.argtypes = [vp, fl, fl, fl]
+    L.gsb_gs_read.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.gsb_gs_enable_grad_dump.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -215,3 +248,146 @@ class TsdfEngine:
 
     def free_image(self):
         return self.read(IMAGE_FREE, np.uint8, (self.h, self.w, 4))
+
+
+PARAM_NAMES = ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities")
+PARAM_WIDTH = dict(means=3, scales=3, quats=4, featuresDc=3, featuresRest=45, opacities=1)
+
+
+class GaussianEngine:
+    """RawGaussianModel / SLAMGaussianModel with render_method "ges" (reference include/raw_gs_model.h:8-298): same parameter
+    tensors (means, scales=log, quats=wxyz, featuresDc, featuresRest [N,15,3], opacities=logit [N,1]), forward(cam, ref_depth,
+    base_color), one fused optimiser iteration (forward + computeLoss + backward + optimizersStep), initOptimizers, prunePoints,
+    add.  Arguments are numpy arrays (copied) or torch CUDA tensors (used in place)."""
+
+    def __init__(self, width, height, capacity=1 << 21, device=0, **overrides):
+        L = load_library()
+        self.L = L
+        cfg = GsConfig()
+        L.gsb_gs_default_config(C.byref(cfg))
+        cfg.width, cfg.height, cfg.capacity, cfg.device = width, height, capacity, device
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise EngineError("unknown Gaussian-engine option %r" % k)
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.W, self.H = width, height
+        self.tile_w, self.tile_h = (width + 15) // 16, (height + 15) // 16
+        h = C.c_void_p()
+        _check(L.gsb_gs_create(C.byref(cfg), C.byref(h)))
+        self.h_ = h
+
+    def close(self):
+        if getattr(self, "h_", None):
+            self.L.gsb_gs_destroy(self.h_)
+            self.h_ = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.L.gsb_gs_set_stream(self.h_, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        _check(self.L.gsb_gs_sync(self.h_))
+
+    @staticmethod
+    def _arr(params):
+        out = []
+        for k in PARAM_NAMES:
+            a = params.get(k)
+            if a is None:
+                out.append(None)
+            elif isinstance(a, np.ndarray):
+                out.append(np.ascontiguousarray(a, dtype=np.float32))
+            else:
+                out.append(a.contiguous())
+        return out
+
+    def set_params(self, params):
+        a = self._arr(params)
+        n = int(a[0].shape[0])
+        _check(self.L.gsb_gs_set_params(self.h_, n, *[_ptr(x) for x in a]))
+
+    def add(self, params):
+        a = self._arr(params)
+        n = int(a[0].shape[0])
+        _check(self.L.gsb_gs_append(self.h_, n, *[_ptr(x) for x in a]))
+
+    def getGaussianNum(self):
+        v = C.c_int(0)
+        _check(self.L.gsb_gs_count(self.h_, C.byref(v)))
+        return v.value
+
+    def get_params(self):
+        n = self.getGaussianNum()
+        out = {k: np.empty((n, PARAM_WIDTH[k]), np.float32) for k in PARAM_NAMES}
+        _check(self.L.gsb_gs_get_params(self.h_, n, *[_ptr(out[k]) for k in PARAM_NAMES]))
+        out["featuresRest"] = out["featuresRest"].reshape(n, 15, 3)
+        return out
+
+    def initOptimizers(self):
+        _check(self.L.gsb_gs_init_optimizers(self.h_))
+
+    def set_learning_rates(self, means, scales, quats, dc, rest, opac):
+        _check(self.L.gsb_gs_set_learning_rates(self.h_, means, scales, quats, dc, rest, opac))
+
+    @staticmethod
+    def _cam(c2w):
+        return np.ascontiguousarray(c2w, dtype=np.float32).reshape(16)
+
+    def forward(self, c2w, intr, ref_depth_dev, base_color_dev, rgb_out, depth_out, alpha_out):
+        """gesForward without autograd; all image arguments are device tensors / pointers"""
+        c = self._cam(c2w)
+        _check(self.L.gsb_gs_render(self.h_, _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(ref_depth_dev), _ptr(base_color_dev),
+                                    _ptr(rgb_out), _ptr(depth_out), _ptr(alpha_out)))
+
+    def train_step(self, c2w, intr, ref_depth_dev, base_color_dev, gt_rgb_dev):
+        c = self._cam(c2w)
+        _check(self.L.gsb_gs_train_step(self.h_, _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(ref_depth_dev),
+                                        _ptr(base_color_dev), _ptr(gt_rgb_dev)))
+
+    def loss(self):
+        v = C.c_double(0)
+        _check(self.L.gsb_gs_loss(self.h_, C.byref(v)))
+        return v.value
+
+    def prunePoints(self, min_opac, min_scale, max_scale):
+        _check(self.L.gsb_gs_prune(self.h_, min_opac, min_scale, max_scale))
+
+    def enable_grad_dump(self, on=True):
+        _check(self.L.gsb_gs_enable_grad_dump(self.h_, int(on)))
+
+    def read(self, what, dtype, shape):
+        out = np.empty(shape, dtype=dtype)
+        _check(self.L.gsb_gs_read(self.h_, what, _ptr(out), out.nbytes))
+        return out
+
+    def counters(self):
+        return self.read(GS_COUNTERS, np.int32, (8,))
+
+    def splat_records(self, n):
+        r = self.read(GS_SPLAT_RECORDS, np.float32, (n, 12))
+        radii = r[:, 3].copy().view(np.int32)
+        vis = radii > 0
+        z = lambda a: np.where(vis[:, None] if a.ndim == 2 else vis, a, 0)
+        return dict(radii=radii, means2d=z(r[:, 0:2]), opacities=z(r[:, 2]), conics=z(r[:, 4:7]), depths=z(r[:, 7]), colors=z(r[:, 8:11]),
+                    flags=np.where(vis, r[:, 11].copy().view(np.int32), 0))
+
+    def splat_grads(self, n):
+        g = self.read(GS_SPLAT_GRADS, np.float32, (n, 12))
+        return dict(v_means2d=g[:, 0:2], v_opacities=g[:, 2], v_depths=g[:, 3], v_conics=g[:, 4:7], v_colors=g[:, 8:11])
+
+    def tile_bins(self):
+        off = self.read(GS_TILE_OFFSETS, np.int32, (self.tile_w * self.tile_h + 1,))
+        ids = self.read(GS_FLATTEN_IDS, np.int32, (int(off[-1]),)) if off[-1] > 0 else np.zeros(0, np.int32)
+        return off, ids
+
+    def v_out(self):
+        return self.read(GS_V_OUT, np.float32, (self.H, self.W, 4))
+
+    def param_grads(self, n):
+        ids = dict(means=GS_GRAD_MEANS, scales=GS_GRAD_SCALES, quats=GS_GRAD_QUATS, featuresDc=GS_GRAD_DC, featuresRest=GS_GRAD_REST,
+                   opacities=GS_GRAD_OPAC)
+        out = {k: self.read(ids[k], np.float32, (n, PARAM_WIDTH[k])) for k in PARAM_NAMES}
+        out["featuresRest"] = out["featuresRest"].reshape(n, 15, 3)
+        return out

@@ -108,6 +108,75 @@ int gsb_tsdf_counter(gsb_tsdf_t *e, int which, int *value);
  * stage: 0 allocate (B1-B4), 1 integrate (B5), 2 expected depth (B6), 3 raycast (B7), 4 ICP maps (B8) */
 int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage);
 
+/* ===================================================================================================
+ * A.  Gaussian model  -- replaces RawGaussianModel / SLAMGaussianModel with render_method == "ges"
+ *     (reference include/raw_gs_model.h:8-298, src/raw_gs_model.cpp:188-417, 654-705; slam/slam_gs_model.cpp:5-56)
+ *     and, underneath, the gsplat autograd wrappers it calls (gsplat/gsplat_wapper.hpp:16-620):
+ *     FullyFusedProjection, SphericalHarmonicsNew, isectTilesNoDepth, isectOffsetEncodeNoDepth,
+ *     RasterizeToPixelsGes_NewParallel, plus 6 x torch::optim::Adam.
+ *     Parameters are the reference's tensors: means [N,3], scales [N,3] (log), quats [N,4] (w,x,y,z), featuresDc [N,3],
+ *     featuresRest [N,15,3], opacities [N,1] (logit); fp32, row-major, contiguous.
+ *     Cameras: c2w = 16 floats ROW-major camera-to-world (cam.c2w_slam as torch stores it), pinhole fx, fy, cx, cy.
+ * =================================================================================================== */
+typedef struct gsb_gs gsb_gs_t;
+
+typedef struct gsb_gs_config
+{
+    int width, height;
+    int capacity;                 /* maximum number of Gaussians (buffers are allocated once)                          */
+    int isect_capacity;           /* maximum Gaussian-tile intersections per render                                    */
+    int item_capacity;            /* maximum backward work items per render (one per 2048 box pixels of a splat)       */
+    int max_gs_radii;             /* MODEL.max_gs_radii (office0.yaml:83); <= 0 disables the clamp                     */
+    float delta_depth;            /* MODEL.delta_depth                                                                 */
+    float eps2d, near_plane, far_plane, radius_clip;   /* include/raw_gs_model.h rendering constants                   */
+    float lr_means, lr_scales, lr_quats, lr_dc, lr_rest, lr_opac;   /* MODEL.*_lr (office0.yaml:93-100)                */
+    float scene_scale;            /* multiplies lr_means (src/raw_gs_model.cpp:666)                                    */
+    int device;
+} gsb_gs_config_t;
+
+void gsb_gs_default_config(gsb_gs_config_t *cfg);
+int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out);
+void gsb_gs_destroy(gsb_gs_t *e);
+int gsb_gs_set_stream(gsb_gs_t *e, void *cuda_stream);
+int gsb_gs_sync(gsb_gs_t *e);
+
+/* parameter I/O; pointers may be host or device memory. rest may be NULL (zeros). */
+int gsb_gs_set_params(gsb_gs_t *e, int n, const float *means, const float *scales_log, const float *quats, const float *dc,
+                      const float *rest, const float *opac_logit);
+int gsb_gs_append(gsb_gs_t *e, int n, const float *means, const float *scales_log, const float *quats, const float *dc,
+                  const float *rest, const float *opac_logit);            /* RawGaussianParams::add                     */
+int gsb_gs_get_params(gsb_gs_t *e, int n, float *means, float *scales_log, float *quats, float *dc, float *rest, float *opac_logit);
+int gsb_gs_count(gsb_gs_t *e, int *n);                                    /* getGaussianNum(); synchronises             */
+int gsb_gs_count_upper(gsb_gs_t *e);                                      /* host-side bound, no synchronisation        */
+
+int gsb_gs_init_optimizers(gsb_gs_t *e);                                  /* RawGaussianModel::initOptimizers           */
+int gsb_gs_set_learning_rates(gsb_gs_t *e, float means, float scales, float quats, float dc, float rest, float opac);
+
+/* RawGaussianModel::forward (gesForward), no grad: rgb [H,W,3], depth [H,W], alpha (weight sum) [H,W], device pointers.
+ * ref_depth [H,W] and base_color [H,W,3] are the TSDF raycast maps (runRaycastByCam depth_map / color_map). */
+int gsb_gs_render(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
+                  const float *base_color_dev, float *rgb_dev, float *depth_dev, float *alpha_dev);
+/* one iteration of SLAMPipeline::localOptimize: forward + L1 loss vs gt_rgb [H,W,3] + backward + Adam step + zero grad */
+int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
+                      const float *base_color_dev, const float *gt_rgb_dev);
+int gsb_gs_loss(gsb_gs_t *e, double *loss);                               /* loss["total"] of the last step; synchronises */
+/* SLAMPipeline::removeRedundantGs + prunePoints (remove_configs.low_opac_thres, small_scale_thres, large_scale_thres) */
+int gsb_gs_prune(gsb_gs_t *e, float min_opac, float min_scale, float max_scale);
+
+/* state read-back for parity tests (synchronises) */
+enum
+{
+    GSB_GS_SPLAT_RECORDS = 0,   /* [N] 12 floats: mean2d.xy, opacity, radius(int) | conic abc, depth | rgb, flags(int)   */
+    GSB_GS_SPLAT_GRADS = 1,     /* [N] 12 floats: v_mean2d.xy, v_opacity, v_depth | v_conic abc, 0 | v_rgb, 0            */
+    GSB_GS_TILE_OFFSETS = 2,    /* int[T+1]  (isect_offsets + n_isects)                                                  */
+    GSB_GS_FLATTEN_IDS = 3,     /* int[n_isects]                                                                         */
+    GSB_GS_V_OUT = 4,           /* float4[H*W]: dL/d render rgb, dL/d alpha                                              */
+    GSB_GS_COUNTERS = 5,        /* int[8]: n_isects, n_items, overflow bits, -, n_visible, ...                           */
+    GSB_GS_GRAD_MEANS = 6, GSB_GS_GRAD_SCALES = 7, GSB_GS_GRAD_QUATS = 8, GSB_GS_GRAD_DC = 9, GSB_GS_GRAD_REST = 10, GSB_GS_GRAD_OPAC = 11
+};
+int gsb_gs_read(gsb_gs_t *e, int what, void *dst_host, size_t bytes);
+int gsb_gs_enable_grad_dump(gsb_gs_t *e, int on);   /* keep the parameter gradients of each train step for GSB_GS_GRAD_* */
+
 #ifdef __cplusplus
 }
 #endif

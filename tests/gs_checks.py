@@ -1,0 +1,115 @@
+"""GPU-vs-oracle comparison of the gsplat-GES path, shared by tests/test_gs_parity_gpu.py and __graft_entry__.smoke().
+
+Tolerances (fp32; the oracle is numpy without FMA contraction, the rasteriser uses FMA and __expf like the reference):
+  * radii, tile offsets, flatten ids: bit-exact;
+  * projection outputs (means2d, conics, depths), colours, opacities: rtol 2e-5 / atol 2e-6 (they only differ through expf);
+  * rendered rgb / depth / alpha, dL/d(render): |d| <= 2e-4 + 2e-4 |ref| for all but a 2e-4 fraction of pixels -- a splat
+    whose alpha sits within one ulp of the 1/255 cut may legitimately fall on either side;
+  * per-splat raster gradients and parameter gradients: max |d| <= 2e-3 of the largest magnitude of that tensor;
+  * parameters after the Adam step: compared with the oracle's Adam applied to the GPU's own gradients (rtol 1e-5), so a
+    sign flip of a near-zero gradient (which moves a parameter by a full +-lr under Adam) cannot masquerade as an error.
+"""
+import numpy as np
+import torch
+
+from oracle import gs_oracle as go
+from tests.helpers_gs import camera, random_splats, scene_images
+
+LR = dict(means=1.6e-4, scales=5e-3, quats=1e-3, featuresDc=2.5e-3, featuresRest=5e-4, opacities=5e-2)
+
+
+def close_frac(name, a, b, atol, rtol, max_bad_frac=0.0):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (name, a.shape, b.shape)
+    bad = np.abs(a - b) > atol + rtol * np.abs(b)
+    frac = bad.mean() if bad.size else 0.0
+    assert frac <= max_bad_frac, "%s: %.3g of elements differ (max |d| = %.3g at ref %.3g)" % (
+        name, frac, np.abs(a - b).max(), np.abs(b).max())
+
+
+def close_scaled(name, a, b, tol):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (name, a.shape, b.shape)
+    scale = np.abs(b).max() + 1e-20
+    err = np.abs(a - b).max() / scale
+    assert err <= tol, "%s: max |d| / max |ref| = %.3g (scale %.3g)" % (name, err, scale)
+
+
+def intr_of(K, W, H):
+    return dict(width=W, height=H, fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]))
+
+
+def compare_iteration(N, W, H, seed, verbose=False, **splat_kw):
+    from gps_slam_b200.engine import GaussianEngine
+    p = random_splats(N, seed=seed, **splat_kw)
+    c2w, K = camera(W, H, seed)
+    ref_depth, base, gt = scene_images(W, H, seed)
+    it = go.ges_iteration(p, c2w, K, W, H, ref_depth, base, gt)
+    intr = intr_of(K, W, H)
+    dev = torch.device("cuda", 0)
+    rd_d, base_d, gt_d = [torch.from_numpy(a).to(dev).contiguous() for a in (ref_depth, base, gt)]
+    eng = GaussianEngine(W, H, capacity=max(N, 1))
+    try:
+        eng.set_params(p)
+        assert eng.getGaussianNum() == N
+        eng.enable_grad_dump(True)
+        eng.initOptimizers()
+        # ---- gesForward (no grad)
+        rgb = torch.empty((H, W, 3), device=dev)
+        depth = torch.empty((H, W), device=dev)
+        alpha = torch.empty((H, W), device=dev)
+        eng.forward(c2w, intr, rd_d, base_d, rgb, depth, alpha)
+        eng.sync()
+        rec = eng.splat_records(N)
+        proj = it["proj"]
+        assert np.array_equal(rec["radii"], proj["radii"]), "radii differ at %s" % np.nonzero(rec["radii"] != proj["radii"])[0][:5]
+        close_frac("means2d", rec["means2d"], proj["means2d"], 2e-4, 2e-6)
+        close_frac("conics", rec["conics"], proj["conics"], 2e-6, 2e-5)
+        close_frac("depths", rec["depths"], proj["depths"], 2e-6, 2e-6)
+        vis = proj["radii"] > 0
+        close_frac("colors", rec["colors"][vis], it["colors"][vis], 2e-6, 2e-5)
+        close_frac("opacities", rec["opacities"][vis], go.real_opacities(p["opacities"]).reshape(-1)[vis], 2e-6, 2e-5)
+        off, ids = eng.tile_bins()
+        assert off[-1] == len(it["isect_ids"]), "n_isects %d vs %d" % (off[-1], len(it["isect_ids"]))
+        assert np.array_equal(off[:-1], it["tile_offsets"]), "tile offsets differ"
+        assert np.array_equal(ids, it["flatten_ids"]), "flatten ids differ"
+        close_frac("rgb", rgb.cpu().numpy(), it["rgb"], 2e-4, 2e-4, 2e-4)
+        close_frac("alpha", alpha.cpu().numpy(), it["alphas"], 2e-4, 2e-4, 2e-4)
+        ok = np.isfinite(it["depth"])
+        close_frac("depth", depth.cpu().numpy()[ok], it["depth"][ok], 2e-4, 2e-4, 2e-4)
+        # ---- one optimiser iteration
+        eng.train_step(c2w, intr, rd_d, base_d, gt_d)
+        loss = eng.loss()
+        assert abs(loss - it["loss"]) <= 1e-5 * max(1.0, abs(it["loss"])), "loss %r vs %r" % (loss, it["loss"])
+        vo = eng.v_out()
+        close_frac("v_render", vo[..., :3], it["v_render"][..., :3], 1e-9, 2e-4, 2e-4)
+        close_frac("v_alpha", vo[..., 3], it["v_alphas"], 1e-9, 2e-4, 2e-4)
+        sg = eng.splat_grads(N)
+        for k in ("v_means2d", "v_conics", "v_opacities"):
+            close_scaled(k, sg[k][vis], it[k][vis], 2e-3)
+        close_scaled("v_colors", sg["v_colors"][vis], it["v_colors"][vis, :3], 2e-3)
+        pg = eng.param_grads(N)
+        for k in ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities"):
+            close_scaled("grad " + k, pg[k].reshape(N, -1), it["grads"][k].reshape(N, -1), 3e-3)
+        after = eng.get_params()
+        for k in ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities"):
+            exp = np.array(p[k], np.float32, copy=True).reshape(N, -1)
+            g = pg[k].reshape(N, -1)
+            m, v = np.zeros_like(exp), np.zeros_like(exp)
+            go.adam_step(exp, g, m, v, 1, LR[k])
+            # Gaussians outside the frustum never get optimiser state and must be untouched bit for bit
+            got = after[k].reshape(N, -1)
+            assert np.array_equal(got[~vis], np.asarray(p[k], np.float32).reshape(N, -1)[~vis]), "culled Gaussians moved: " + k
+            close_frac("adam " + k, got[vis], exp[vis], 1e-7, 1e-5)
+        cnt = eng.counters()
+        assert cnt[2] == 0, "capacity overflow flags %d" % cnt[2]
+        if verbose:
+            print("smoke gs: N=%d visible=%d isects=%d loss=%.6f -- bins bit-exact, render/grad/Adam within tolerance of the oracle" % (
+                N, int(vis.sum()), int(off[-1]), loss))
+    finally:
+        eng.close()
+    return it
+
+
+def smoke_check(verbose=False):
+    compare_iteration(1500, 320, 192, seed=7, verbose=verbose)
