@@ -15,6 +15,7 @@ all host threads) on a bounded sample of the same frames.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -157,6 +158,26 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def eval_psnr(pipe, intr, poses, rgba, n_frames, dev, every=10):
+    """renderEvalImgs on every `every`-th training camera: PSNR = 20 log10(1 / sqrt(mse)) of the composited render against the
+    frame (scripts/utils/image_utils.py psnr), and of the TSDF colour raycast alone for context.  Not timed."""
+    import torch
+    H, W = intr["height"], intr["width"]
+    rgb = torch.empty((H, W, 3), device=dev)
+    depth = torch.empty((H, W), device=dev)
+    alpha = torch.empty((H, W), device=dev)
+    ps, ps_tsdf = [], []
+    with torch.cuda.stream(pipe.stream):
+        for i in range(0, n_frames, every):
+            base = pipe.render_eval(poses[i], rgb, depth, alpha)
+            gt = rgba[i][..., :3].float() / 255.0
+            mse = float(((rgb.clamp(0, 1) - gt) ** 2).mean())
+            mse_t = float(((base - gt) ** 2).mean())
+            ps.append(20.0 * math.log10(1.0 / math.sqrt(mse)))
+            ps_tsdf.append(20.0 * math.log10(1.0 / math.sqrt(mse_t)))
+    return {"psnr_db": sum(ps) / len(ps), "psnr_tsdf_only_db": sum(ps_tsdf) / len(ps_tsdf), "cameras": len(ps)}
+
+
 def cpu_baseline(intr, poses, rgba, depth, n_frames=6):
     import numpy as np
     from gps_slam_b200 import synthetic as syn
@@ -249,6 +270,7 @@ def main():
 
     ms, launches, clocks = run_leg(True)
     stats = pipe.stats()
+    psnr = eval_psnr(pipe, intr, poses, rgba, n_frames, dev) if mode == "train" else None
     ms_e2e, _, _ = run_leg(False)
     frames = args.steps * FRAMES_PER_STEP
     fps = frames / (ms * 1e-3)
@@ -271,7 +293,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": dict({"workload": slam.workload_name(mode), "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
                             "l2": "no explicit flush: every frame is new input (4.9 MB) and each step streams the visible voxel "
-                                  "blocks 10x (V x 8 KB per frame), working set > 126 MB L2"}, **stats),
+                                  "blocks 10x (V x 8 KB per frame), working set > 126 MB L2", "quality": psnr}, **stats),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline, "cpu_baseline": cpu,

@@ -19,6 +19,7 @@ SOURCES = [
     ("icp_kernels.cu", ["-fmad=false"]),
     ("gs_project.cu", ["-fmad=false"]),
     ("gs_raster.cu", []),
+    ("gs_spawn.cu", ["-fmad=false"]),
     ("gs_engine.cu", ["-fmad=false"]),
 ]
 

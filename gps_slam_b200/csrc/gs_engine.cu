@@ -12,6 +12,7 @@
 #include "../../include/gpsslam_b200.h"
 #include "common.cuh"
 #include "gs.h"
+#include "gs_spawn.h"
 
 using namespace gs;
 
@@ -33,10 +34,15 @@ struct gsb_gs
     float *lossTile;
     double *lossDev;
     int *scanTmp;
+    SpawnBuffers sb;
+    float *spRgb, *spDepth, *spAlpha; // render of the spawn camera (initNewGaussians)
     int adamStep;
     int *hostInts;   // pinned [8]
     double *hostLoss; // pinned
     bool haveDbg;
+    CamParams lastCam; // camera / image set of the last train step or stage-0 call (gsb_gs_run_stage)
+    RasterIO lastIo;
+    bool haveLast;
     std::vector<void *> allocs;
 };
 
@@ -110,6 +116,7 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     e->nUpper = 0;
     e->adamStep = 0;
     e->haveDbg = false;
+    e->haveLast = false;
     e->hostInts = nullptr, e->hostLoss = nullptr;
     GS_CUDA_OK(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
     e->stream = e->ownStream;
@@ -138,6 +145,21 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     rc |= dev_alloc(e, &e->lossTile, (size_t)e->T);
     rc |= dev_alloc(e, &e->lossDev, 1);
     rc |= dev_alloc(e, &e->scanTmp, (size_t)e->cap / 1024 + 2);
+    {
+        unsigned tbl = 1;
+        while (tbl < 2 * P)
+            tbl <<= 1;
+        e->sb.tableMask = tbl - 1;
+        rc |= dev_alloc(e, &e->sb.flags, P);
+        rc |= dev_alloc(e, &e->sb.chunkCnt, P / 1024 + 2);
+        rc |= dev_alloc(e, &e->sb.pixOf, P);
+        rc |= dev_alloc(e, &e->sb.keys, (size_t)tbl);
+        rc |= dev_alloc(e, &e->sb.heads, (size_t)tbl);
+        rc |= dev_alloc(e, &e->sb.next, P);
+        rc |= dev_alloc(e, &e->spRgb, P * 3);
+        rc |= dev_alloc(e, &e->spDepth, P);
+        rc |= dev_alloc(e, &e->spAlpha, P);
+    }
     if (!rc && cudaMallocHost((void **)&e->hostInts, 8 * sizeof(int)) != cudaSuccess)
         rc = gs_set_error(__FILE__, __LINE__, "pinned allocation failed");
     if (!rc && cudaMallocHost((void **)&e->hostLoss, sizeof(double)) != cudaSuccess)
@@ -338,6 +360,7 @@ extern "C" int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float 
     project_sh_fwd(e->p, e->nDev, e->nUpper, cam, e->recs, e->grads, e->bins, e->tileW, e->tileH, true, e->stream);
     bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
     RasterIO io = make_io(e, ref_depth_dev, base_color_dev, gt_rgb_dev);
+    e->lastCam = cam, e->lastIo = io, e->haveLast = true;
     raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
     if (e->nUpper > 0)
         raster_bwd(e->recs, e->bins, e->W, e->H, io, nullptr, e->grads, e->stream);
@@ -419,5 +442,88 @@ extern "C" int gsb_gs_read(gsb_gs_t *e, int what, void *dst, size_t bytes)
         return gs_set_error(__FILE__, __LINE__, "read larger than the buffer");
     GS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
     GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// runRaycastByCam's tensor glue (slam/slam_pipeline.cpp:386-403): from GetFreeVertex()/GetFreeImage() device images to the
+// depth_map [H,W] / color_map [H,W,3] / confidence_map [H,W] (nullable) the Gaussian model consumes.  c2w row-major (cam.c2w).
+extern "C" int gsb_gs_raycast_maps(gsb_gs_t *e, const void *free_vertex_dev, const void *free_image_dev, const float *c2w, float voxel_size,
+                                   float *depth_map_dev, float *color_map_dev, float *conf_map_dev)
+{
+    if (!e || !free_vertex_dev || !free_image_dev || !c2w || !depth_map_dev || !color_map_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    CamParams cam;
+    make_camera(e, c2w, 1.f, 1.f, 0.f, 0.f, cam);
+    float w2c[16] = {cam.R[0], cam.R[1], cam.R[2], cam.t[0], cam.R[3], cam.R[4], cam.R[5], cam.t[1], cam.R[6], cam.R[7], cam.R[8], cam.t[2], 0, 0, 0, 1};
+    raycast_maps(e->W * e->H, (const float4 *)free_vertex_dev, (const uchar4 *)free_image_dev, w2c, voxel_size, depth_map_dev, color_map_dev,
+                 conf_map_dev, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Camera::image (float rgb in [0,1]) and Camera::depth (metres) from the raw frame
+extern "C" int gsb_gs_frame_to_float(gsb_gs_t *e, const void *rgba_dev, const void *depth_mm_dev, float *rgb_dev, float *depth_dev)
+{
+    if (!e || !rgba_dev || !rgb_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    frame_to_float(e->W * e->H, (const uchar4 *)rgba_dev, (const short *)depth_mm_dev, rgb_dev, depth_dev, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// SLAMPipeline::initNewGaussians + SLAMGaussianModel::addGaussians (slam/slam_pipeline.cpp:450-526, slam/slam_gs_model.cpp:5-56):
+// render the current camera (when Gaussians exist), build the sample mask, sample, and append new Gaussians at the raycast
+// vertices.  No host round trip; call gsb_gs_count afterwards to learn the new count.
+extern "C" int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const float *c2w, float fx, float fy, float cx, float cy,
+                            const void *free_vertex_dev, float voxel_size, const float *depth_map_dev, const float *color_map_dev,
+                            const float *gt_rgb_dev)
+{
+    if (!e || !sc || !c2w || !free_vertex_dev || !depth_map_dev || !color_map_dev || !gt_rgb_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    if (!(sc->max_init_scale > 0.f))
+        return gs_set_error(__FILE__, __LINE__, "gsb_gs_spawn needs max_init_scale > 0 (bounded-radius KNN)");
+    if (e->nUpper > 0)
+        if (gsb_gs_render(e, c2w, fx, fy, cx, cy, depth_map_dev, color_map_dev, e->spRgb, e->spDepth, e->spAlpha))
+            return 1;
+    SpawnParams sp;
+    sp.W = e->W, sp.H = e->H, sp.P = e->W * e->H;
+    sp.voxelSize = voxel_size;
+    sp.colorErrorThres = sc->color_error_thres;
+    sp.depthMin = sc->depth_vis_min, sp.depthMax = sc->depth_vis_max, sp.alphaMax = sc->alpha_vis_max;
+    double r = (double)sc->sample_ratio * 4294967296.0;
+    sp.ratioThreshold = r >= 4294967295.0 ? 0xffffffffu : (r <= 0.0 ? 0u : (unsigned)r);
+    sp.seed = sc->seed;
+    sp.maxScale = sc->max_init_scale, sp.minScale = sc->min_init_scale;
+    sp.defaultOpacity = sc->default_opacity;
+    spawn(sp, e->sb, (const float4 *)free_vertex_dev, depth_map_dev, color_map_dev, gt_rgb_dev, e->spRgb, e->spAlpha, e->p, e->nDev, e->cap,
+          e->touched, e->bins.counters, e->stream);
+    // host-side bound until the next gsb_gs_count
+    long long up = (long long)e->nUpper + sp.P;
+    e->nUpper = (int)(up > e->cap ? e->cap : up);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Single stages on the camera / images of the last gsb_gs_train_step, for per-kernel timing (bench.py roofline, ncu).
+// stage: 0 projection+SH (for backward), 1 tile binning, 2 rasteriser forward (train mode), 3 rasteriser backward,
+//        4 drop the backward work list (leaves the engine ready for the next train step).  Run 0,1,2 before 3; finish with 4.
+extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
+{
+    if (!e->haveLast)
+        return gs_set_error(__FILE__, __LINE__, "gsb_gs_run_stage needs a previous gsb_gs_train_step");
+    switch (stage)
+    {
+    case 0:
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.tileCount, 0, sizeof(int) * (e->T + 1), e->stream));
+        project_sh_fwd(e->p, e->nDev, e->nUpper, e->lastCam, e->recs, e->grads, e->bins, e->tileW, e->tileH, true, e->stream);
+        break;
+    case 1: bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream); break;
+    case 2: raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, e->lastIo, e->stream); break;
+    case 3: raster_bwd(e->recs, e->bins, e->W, e->H, e->lastIo, nullptr, e->grads, e->stream); break;
+    case 4: GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream)); break;
+    default: return gs_set_error(__FILE__, __LINE__, "bad stage id");
+    }
+    GS_CUDA_OK(cudaGetLastError());
     return 0;
 }

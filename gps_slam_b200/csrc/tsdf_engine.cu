@@ -47,6 +47,7 @@ struct gsb_tsdf
     int trackingFrames;        // ITMTrackingState::framesProcessed
     int agePointCloud;         // ITMTrackingState::age_pointCloud (-1 = no valid point cloud yet)
     bool haveFrame;
+    const void *lastRgba;      // RGBA frame consumed by the last ProcessFrame (own upload buffer or the caller's resident frame)
     std::vector<void *> allocs;
 };
 
@@ -169,6 +170,7 @@ extern "C" int gsb_tsdf_reset(gsb_tsdf_t *e)
     e->trackingFrames = 0;
     e->agePointCloud = -1;
     e->haveFrame = false;
+    e->lastRgba = nullptr;
     E_CUDA(cudaStreamSynchronize(e->stream));
     E_CUDA(cudaGetLastError());
     return 0;
@@ -238,6 +240,7 @@ static int process_resident(gsb_tsdf *e, const float *gt_c2w)
     e->pose_pointCloud = e->pose_d;
     e->agePointCloud = (e->agePointCloud == -1) ? -2 : 0;
     e->haveFrame = true;
+    e->lastRgba = e->frame.rgba;
     E_CUDA(cudaGetLastError());
     return 0;
 }
@@ -285,6 +288,7 @@ extern "C" int gsb_tsdf_run_raycast(gsb_tsdf_t *e, const float *c2w, float fx, f
     return 0;
 }
 
+extern "C" const void *gsb_tsdf_current_rgba_dev(gsb_tsdf_t *e) { return e->lastRgba; }
 extern "C" const void *gsb_tsdf_free_image_dev(gsb_tsdf_t *e) { return e->imageFree; }
 extern "C" const void *gsb_tsdf_free_vertex_dev(gsb_tsdf_t *e) { return e->rayFree; }
 extern "C" const void *gsb_tsdf_live_vertex_dev(gsb_tsdf_t *e) { return e->rayLive; }

@@ -39,6 +39,12 @@ class GsConfig(C.Structure):
                 ("lr_opac", C.c_float), ("scene_scale", C.c_float), ("device", C.c_int)]
 
 
+class SpawnConfig(C.Structure):
+    _fields_ = [("color_error_thres", C.c_float), ("depth_vis_min", C.c_float), ("depth_vis_max", C.c_float), ("alpha_vis_max", C.c_float),
+                ("sample_ratio", C.c_float), ("max_init_scale", C.c_float), ("min_init_scale", C.c_float), ("default_opacity", C.c_float),
+                ("seed", C.c_uint)]
+
+
 (GS_SPLAT_RECORDS, GS_SPLAT_GRADS, GS_TILE_OFFSETS, GS_FLATTEN_IDS, GS_V_OUT, GS_COUNTERS, GS_GRAD_MEANS, GS_GRAD_SCALES, GS_GRAD_QUATS,
  GS_GRAD_DC, GS_GRAD_REST, GS_GRAD_OPAC) = range(12)
 
@@ -106,6 +112,12 @@ def load_library():
     L.gsb_gs_prune.argtypes = [vp, fl, fl, fl]
     L.gsb_gs_read.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.gsb_gs_enable_grad_dump.argtypes = [vp, C.c_int]
+    L.gsb_gs_run_stage.argtypes = [vp, C.c_int]
+    L.gsb_gs_spawn.argtypes = [vp, C.POINTER(SpawnConfig), vp, fl, fl, fl, fl, vp, fl, vp, vp, vp]
+    L.gsb_gs_raycast_maps.argtypes = [vp, vp, vp, vp, fl, vp, vp, vp]
+    L.gsb_gs_frame_to_float.argtypes = [vp, vp, vp, vp, vp]
+    L.gsb_tsdf_current_rgba_dev.argtypes = [vp]
+    L.gsb_tsdf_current_rgba_dev.restype = vp
     _lib = L
     return L
 
@@ -178,6 +190,10 @@ class TsdfEngine:
 
     def GetFreeVertex(self):
         return self.L.gsb_tsdf_free_vertex_dev(self.h_)
+
+    def current_rgba(self):
+        """device pointer of the RGBA frame the engine last consumed (its own upload buffer, or the caller's resident frame)"""
+        return self.L.gsb_tsdf_current_rgba_dev(self.h_)
 
     def GetLiveVertex(self):
         return self.L.gsb_tsdf_live_vertex_dev(self.h_)
@@ -353,6 +369,28 @@ class GaussianEngine:
 
     def prunePoints(self, min_opac, min_scale, max_scale):
         _check(self.L.gsb_gs_prune(self.h_, min_opac, min_scale, max_scale))
+
+    def raycast_maps(self, free_vertex_ptr, free_image_ptr, c2w, voxel_size, depth_map, color_map, conf_map=None):
+        """runRaycastByCam glue: TSDF free-view vertex/colour images -> depth_map [H,W], color_map [H,W,3] (device tensors)"""
+        c = self._cam(c2w)
+        _check(self.L.gsb_gs_raycast_maps(self.h_, _ptr(free_vertex_ptr), _ptr(free_image_ptr), _ptr(c), voxel_size, _ptr(depth_map),
+                                          _ptr(color_map), _ptr(conf_map)))
+
+    def frame_to_float(self, rgba_ptr, depth_mm_ptr, rgb_out, depth_out=None):
+        _check(self.L.gsb_gs_frame_to_float(self.h_, _ptr(rgba_ptr), _ptr(depth_mm_ptr), _ptr(rgb_out), _ptr(depth_out)))
+
+    def addGaussians(self, c2w, intr, free_vertex_ptr, voxel_size, depth_map, color_map, gt_rgb, seed, color_error_thres=0.05,
+                     depth_vis_min=0.0, depth_vis_max=5.0, alpha_vis_max=5.0, sample_ratio=0.25, max_init_scale=0.01, min_init_scale=-1.0,
+                     default_opacity=0.5):
+        """initNewGaussians + addGaussians (defaults: configs/release/replica/office0.yaml)"""
+        sc = SpawnConfig(color_error_thres, depth_vis_min, depth_vis_max, alpha_vis_max, sample_ratio, max_init_scale, min_init_scale,
+                         default_opacity, seed & 0xffffffff)
+        c = self._cam(c2w)
+        _check(self.L.gsb_gs_spawn(self.h_, C.byref(sc), _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(free_vertex_ptr),
+                                   voxel_size, _ptr(depth_map), _ptr(color_map), _ptr(gt_rgb)))
+
+    def run_stage(self, stage):
+        _check(self.L.gsb_gs_run_stage(self.h_, stage))
 
     def enable_grad_dump(self, on=True):
         _check(self.L.gsb_gs_enable_grad_dump(self.h_, int(on)))

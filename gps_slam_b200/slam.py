@@ -1,83 +1,321 @@
-"""Host-side SLAM loop over the C-ABI engines -- the Python mirror of SLAMPipeline::SLAMTrainCams
-(reference slam/slam_pipeline.cpp:52-173) for the parts that sit on the hot path.  bench.py drives it.
+"""Host-side SLAM loop over the C-ABI engines -- the Python mirror of SLAMPipeline (reference slam/slam_pipeline.h:6-94,
+slam/slam_pipeline.cpp) for the parts that sit on the hot path: SLAMTrainCams (:52-173), updateFrameList (:293-360),
+runRaycastByCam (:362-415), localFrameRaycast (:417-448), keyFrameRaycast (:528-561), initNewGaussians (:450-526),
+localOptimize (:195-291), removeRedundantGs (:564-586).  Hyper-parameters are configs/release/replica/office0.yaml.
 
 mode "recon": TSDF fusion only per frame (reference work_mode == "recon", slam_pipeline.cpp:96).
+mode "train": TSDF fusion per frame and, every local_opt_interval frames, window/keyframe raycasts, Gaussian spawn,
+              local_opt_iters optimiser iterations and the prune.
+
+torch is used for device buffers only; every computation is a kernel of libgpsslam_b200.so.
 """
+import collections
+import math
+import random
+
 import numpy as np
 import torch
 
 from . import engine as E
 from . import synthetic as syn
 
-DEFAULT_MODE = "recon"
+DEFAULT_MODE = "train"
+
+# PIPE / MODEL sections of configs/release/replica/office0.yaml
+OFFICE0 = dict(
+    new_gs_sample_ratio=0.25, color_error_thres=0.05, localframe_cam_window_length=2, localframe_cam_window_interval=5,
+    local_opt_iters=20, local_opt_interval=10, keyframe_theta_thres=30.0, keyframe_trans_thres=0.3, keyframe_select_max=7,
+    depth_vis_max=5.0, depth_vis_min=0.0, alpha_vis_max=5.0,
+    large_scale_thres=0.1, small_scale_thres=0.003, low_opac_thres=0.005,
+    max_init_scale=0.01, min_init_scale=-1.0, default_opacities=0.5,
+    voxel_size=0.005, trunc_dist=0.02, viewFrustum_min=0.2, viewFrustum_max=10.0,
+)
 
 
 def workload_name(mode):
     if mode == "recon":
         return "Replica-shaped 1200x680 synthetic RGB-D, work_mode=recon (TSDF fusion + raycast per frame, use_gt_pose=true)"
-    return "Replica office0-shaped 1200x680 synthetic RGB-D, work_mode=train (gsplat GES + TSDF, use_gt_pose=true)"
+    return "Replica office0-shaped 1200x680 synthetic RGB-D, work_mode=train (gsplat GES + TSDF, use_gt_pose=true), office0.yaml hyper-parameters"
+
+
+class Cam:
+    """the fields of the reference's Camera that the hot path reads (include/camera.h): id, c2w (GT), c2w_slam, image"""
+    __slots__ = ("id", "c2w", "c2w_slam", "image", "depth_map", "color_map")
+
+    def __init__(self, idx, c2w, c2w_slam, image):
+        self.id, self.c2w, self.c2w_slam, self.image = idx, c2w, c2w_slam, image
+        self.depth_map = self.color_map = None
+
+
+def rot_compare(Ra, Rb):
+    """rotCompare (src/tensor_math.cpp:302-317), degrees"""
+    c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
+    return math.degrees(math.acos(min(1.0, max(-1.0, float(c)))))
+
+
+class BufferPool:
+    """device image buffers recycled between cycles (the reference allocates fresh tensors per raycast / camera)"""
+
+    def __init__(self, device):
+        self.device, self.free = device, collections.defaultdict(list)
+
+    def get(self, shape):
+        f = self.free[shape]
+        return f.pop() if f else torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def put(self, t):
+        if t is not None:
+            self.free[tuple(t.shape)].append(t)
 
 
 class SlamPipeline:
-    def __init__(self, intr, mode="recon", device=0, stream=None, rank=0, world=1):
+    def __init__(self, intr, mode="train", device=0, stream=None, rank=0, world=1, cfg=None, seed=42, gs_capacity=1 << 21):
         self.intr, self.mode, self.rank, self.world = intr, mode, rank, world
-        self.tsdf = E.TsdfEngine(intr, tracker=0, device=device)
+        self.cfg = dict(OFFICE0, **(cfg or {}))
+        c = self.cfg
+        self.device = torch.device("cuda", device)
+        self.tsdf = E.TsdfEngine(intr, voxel_size=c["voxel_size"], mu=c["trunc_dist"], view_frustum_min=c["viewFrustum_min"],
+                                 view_frustum_max=c["viewFrustum_max"], tracker=0, device=device)
+        self.W, self.H = intr["width"], intr["height"]
+        self.gs = E.GaussianEngine(self.W, self.H, capacity=gs_capacity, device=device) if mode == "train" else None
         self.stream = stream
         if stream is not None:
             self.tsdf.set_stream(stream.cuda_stream)
-        self.W, self.H = intr["width"], intr["height"]
-        self._pose_host = np.zeros(16, np.float32)
-        self._vis_sum, self._vis_n = 0, 0
+            if self.gs:
+                self.gs.set_stream(stream.cuda_stream)
+        self.pool = BufferPool(self.device)
+        self.seed = seed
+        self.reset()
 
+    # ------------------------------------------------------------------------------------------------------------
     def reset(self):
         self.tsdf.resetAll()
-        self._vis_sum, self._vis_n = 0, 0
+        if self.gs:
+            self.gs.set_params(dict(means=np.zeros((0, 3), np.float32), scales=np.zeros((0, 3), np.float32), quats=np.zeros((0, 4), np.float32),
+                                    featuresDc=np.zeros((0, 3), np.float32), featuresRest=np.zeros((0, 45), np.float32),
+                                    opacities=np.zeros((0, 1), np.float32)))
+        for cam in list(getattr(self, "window", [])) + list(getattr(self, "keyframes", [])):
+            self._release(cam)
+        self.window = collections.deque()
+        self.keyframes = []
+        self.opt_cams = []
+        self.rng = random.Random(self.seed)   # RandomSelector's std::random_device, pinned so that runs repeat
+        self.curr = None
+        self.n_gauss = 0
+        self.cycles = 0
+        self.last_loss = None
+        self.spawned_last = 0
+        self._pose_host = np.zeros(16, np.float32)
 
     def close(self):
         self.tsdf.close()
+        if self.gs:
+            self.gs.close()
 
+    def _release(self, cam):
+        self.pool.put(cam.depth_map)
+        self.pool.put(cam.color_map)
+        cam.depth_map = cam.color_map = None
+
+    # ------------------------------------------------------------------------------------------------------------
     def process_frame(self, idx, rgba_all, depth_all, poses, resident):
-        c2w = syn.c2w_to_colmajor(poses[idx])
+        """one iteration of the SLAMTrainCams loop body (slam_pipeline.cpp:69-143)"""
+        c2w = np.asarray(poses[idx], np.float32)
         if resident:
-            self.tsdf.ProcessFrameDevice(rgba_all[idx], depth_all[idx], c2w)
+            self.tsdf.ProcessFrameDevice(rgba_all[idx], depth_all[idx], syn.c2w_to_colmajor(c2w))
         else:
-            self.tsdf.ProcessFrame(rgba_all[idx], depth_all[idx], c2w)
+            self.tsdf.ProcessFrame(rgba_all[idx], depth_all[idx], syn.c2w_to_colmajor(c2w))
+        if self.mode == "recon":
+            return
+        est = self.tsdf.pose()[1].reshape(4, 4).T.copy()      # est_pose = pose_d->GetInvM() as a row-major tensor (:81-82)
+        self.curr = (idx, c2w, est)
+        self._update_frame_list(idx, c2w, est)
+        c = self.cfg
+        if idx % c["local_opt_interval"] == 0 and idx > 0:
+            self._key_frame_raycast()
+            self._local_frame_raycast()
+            self._init_new_gaussians()
+            self._local_optimize()
+            self._remove_redundant()
+            self.cycles += 1
 
+    def _make_cam(self, idx, c2w, est):
+        """curr_cam.toGPU(): float image of the current frame (slam_pipeline.cpp:84)"""
+        img = self.pool.get((self.H, self.W, 3))
+        self.gs.frame_to_float(self.tsdf.current_rgba(), None, img, None)
+        return Cam(idx, c2w, est, img)
+
+    def _update_frame_list(self, idx, c2w, est):
+        """updateFrameList (slam_pipeline.cpp:293-360)"""
+        if idx == 0:
+            return
+        c = self.cfg
+        cam = None
+        if idx % c["localframe_cam_window_interval"] == 0:
+            cam = self._make_cam(idx, c2w, est)
+            self.window.append(cam)
+            if len(self.window) == c["localframe_cam_window_length"] + 1:
+                old = self.window.popleft()
+                if not any(k is old for k in self.keyframes):
+                    self._release(old)
+                    self.pool.put(old.image)
+        is_key = False
+        if not self.keyframes:
+            is_key = True
+        else:
+            last = self.keyframes[-1]
+            theta = rot_compare(last.c2w_slam[:3, :3].astype(np.float64), est[:3, :3].astype(np.float64))
+            trans = float(np.linalg.norm(last.c2w_slam[:3, 3] - est[:3, 3]))
+            is_key = theta > c["keyframe_theta_thres"] or trans > c["keyframe_trans_thres"]
+        if is_key:
+            self.keyframes.append(cam if cam is not None else self._make_cam(idx, c2w, est))
+
+    def _raycast_by_cam(self, cam):
+        """runRaycastByCam (slam_pipeline.cpp:362-415): free-view raycast at the engine's logged pose of that frame + tensor glue"""
+        self.tsdf.runRaycast(syn.c2w_to_colmajor(cam.c2w_slam), self.intr)
+        if cam.depth_map is None:
+            cam.depth_map = self.pool.get((self.H, self.W))
+            cam.color_map = self.pool.get((self.H, self.W, 3))
+        self.gs.raycast_maps(self.tsdf.GetFreeVertex(), self.tsdf.GetFreeImage(), cam.c2w, self.tsdf.getVoxelSize(), cam.depth_map, cam.color_map)
+
+    def _key_frame_raycast(self):
+        """keyFrameRaycast, sample_method == "random" (slam_pipeline.cpp:528-561): up to keyframe_select_max keyframes drawn
+        without replacement.  Issued BEFORE the window raycasts (the reference does the window first): a free-view raycast does
+        not modify the map, so the order is free, and this way the engine's vertex image still belongs to the newest window
+        camera when the spawn reads it."""
+        k = min(self.cfg["keyframe_select_max"], len(self.keyframes))
+        pool = list(self.keyframes)
+        picked = []
+        for _ in range(k):
+            i = self.rng.randrange(len(pool))
+            cam = pool[i]
+            pool[i] = pool[-1]
+            pool.pop()
+            self._raycast_by_cam(cam)
+            picked.append(cam)
+        self.opt_cams = list(self.window) + picked
+
+    def _local_frame_raycast(self):
+        """localFrameRaycast (slam_pipeline.cpp:417-448)"""
+        for cam in self.window:
+            self._raycast_by_cam(cam)
+
+    def _init_new_gaussians(self):
+        """initNewGaussians + addGaussians on the newest window camera (slam_pipeline.cpp:115, :450-526)"""
+        cam = self.window[-1]
+        c = self.cfg
+        before = self.n_gauss
+        self.gs.addGaussians(cam.c2w_slam, self.intr, self.tsdf.GetFreeVertex(), self.tsdf.getVoxelSize(), cam.depth_map, cam.color_map,
+                             cam.image, seed=self.seed * 7919 + cam.id, color_error_thres=c["color_error_thres"],
+                             depth_vis_min=c["depth_vis_min"], depth_vis_max=c["depth_vis_max"], alpha_vis_max=c["alpha_vis_max"],
+                             sample_ratio=c["new_gs_sample_ratio"], max_init_scale=c["max_init_scale"], min_init_scale=c["min_init_scale"],
+                             default_opacity=c["default_opacities"])
+        self.n_gauss = self.gs.getGaussianNum()    # the one host round trip of the cycle (sizes the next 20 iterations' launches)
+        self.spawned_last = self.n_gauss - before
+
+    def _local_optimize(self):
+        """localOptimize (slam_pipeline.cpp:195-291)"""
+        self.gs.initOptimizers()
+        cams = self.opt_cams
+        current = list(range(len(cams)))
+        for _ in range(self.cfg["local_opt_iters"]):
+            if not current:
+                current = list(range(len(cams)))
+            i = self.rng.randrange(len(current))
+            ci = current[i]
+            current[i] = current[-1]
+            current.pop()
+            cam = cams[ci]
+            self.gs.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image)
+
+    def _remove_redundant(self):
+        c = self.cfg
+        self.gs.prunePoints(c["low_opac_thres"], c["small_scale_thres"], c["large_scale_thres"])
+
+    # ------------------------------------------------------------------------------------------------------------
     def end_of_step(self, resident):
         if not resident:
-            # the call a user makes after a cycle: read the pose estimate back (est_pose, slam_pipeline.cpp:81-82)
+            # what a caller reads back after a cycle: the pose estimate and the last loss (slam_pipeline.cpp:81-82, progress bar :283)
             self.tsdf.sync()
             self._pose_host = self.tsdf.pose()[1]
+            if self.gs and self.cycles:
+                self.last_loss = self.gs.loss()
+
+    def render_eval(self, c2w, rgb, depth, alpha):
+        """renderEvalImgs body for one camera (slam_pipeline.cpp:588-660): free-view raycast + gesForward"""
+        cam = Cam(-1, np.asarray(c2w, np.float32), np.asarray(c2w, np.float32), None)
+        self._raycast_by_cam(cam)
+        self.gs.forward(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, rgb, depth, alpha)
+        base = cam.color_map.clone()
+        self._release(cam)
+        return base
 
     def stats(self):
-        return {"visible_blocks_last_frame": self.tsdf.counter(2), "allocated_blocks": self.tsdf.num_blocks - 1 - self.tsdf.counter(0)}
+        s = {"visible_blocks_last_frame": self.tsdf.counter(2), "allocated_blocks": self.tsdf.num_blocks - 1 - self.tsdf.counter(0)}
+        if self.gs:
+            cnt = self.gs.counters()
+            s.update(gaussians=self.gs.getGaussianNum(), keyframes=len(self.keyframes), opt_cameras=len(self.opt_cams),
+                     last_isects=int(cnt[0]), last_visible=int(cnt[4]), overflow_flags=int(cnt[2]), cycles=self.cycles)
+        return s
 
     def io_bytes_per_step(self, frames_per_step):
-        return frames_per_step * self.W * self.H * 6, 64
+        return frames_per_step * self.W * self.H * 6, 64 + (8 if self.gs else 0)
 
     def scaling(self):
         return "weak"
 
-    def time_dominant_kernel(self, stream, peak_gbs, reps=20):
-        """integrate kernel: algorithmic bytes V*(4+16+2*4096) + 8*P, CUDA events on the launching stream,
-        L2 flushed between launches"""
-        V = self.tsdf.counter(2)
-        P = self.W * self.H
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    def _time(self, stream, fn, reps, flush):
         ms = []
         with torch.cuda.stream(stream):
-            for _ in range(3):
-                self.tsdf.run_stage(1)
+            for _ in range(2):
+                fn()
             for _ in range(reps):
                 flush.fill_(1)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                self.tsdf.run_stage(1)
+                fn()
                 e1.record(stream)
                 e1.synchronize()
                 ms.append(e0.elapsed_time(e1))
-        t = float(np.mean(ms)) * 1e-3
-        alg = V * (4 + 16 + 2 * 4096) + 8 * P
+        return float(np.mean(ms)) * 1e-3
+
+    def time_dominant_kernel(self, stream, peak_gbs, reps=20):
+        """Per-kernel device times (CUDA events on the launching stream, L2 flushed by a 256 MiB fill between launches) and the
+        roofline entry of the kernel BASELINE.json names: the rasteriser backward in train mode (algorithmic bytes
+        24*P + 48*I + 80*N_vis), the TSDF integrate kernel in recon mode (V*(4+16+2*4096) + 8*P)."""
+        P = self.W * self.H
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+        V = self.tsdf.counter(2)
+        table = {}
+        for name, st in (("tsdf_allocate(6 kernels)", 0), ("tsdf_integrate", 1), ("tsdf_expected_depth(2)", 2), ("tsdf_raycast", 3),
+                         ("tsdf_icp_maps", 4)):
+            table[name] = self._time(stream, lambda st=st: self.tsdf.run_stage(st), reps, flush) * 1e6
+        t_int = table["tsdf_integrate"] * 1e-6
+        alg_int = V * (4 + 16 + 2 * 4096) + 8 * P
+        integrate = {"kernel": "k_integrate_tma", "bound": "hbm", "achieved": alg_int / t_int / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": alg_int / t_int / 1e9 / peak_gbs, "traffic": None, "algorithmic_bytes": alg_int, "avg_launch_us": t_int * 1e6,
+                     "units": {"visible_blocks": V, "pixels": P}}
+        live = [c for c in self.opt_cams if c.depth_map is not None and c.image is not None]
+        if self.mode != "train" or not live or self.n_gauss == 0:
+            integrate["kernels_us"] = table
+            return integrate
+        g = self.gs
+        cam = live[-1]
+        with torch.cuda.stream(stream):
+            g.initOptimizers()
+            g.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image)
+        for name, st in (("gs_project_sh", 0), ("gs_bin_tiles(3 kernels)", 1), ("gs_raster_fwd_train", 2), ("gs_raster_bwd", 3)):
+            table[name] = self._time(stream, lambda st=st: g.run_stage(st), reps, flush) * 1e6
+        with torch.cuda.stream(stream):
+            g.run_stage(4)
+        table["gs_train_step(7 kernels, no flush)"] = self._time(
+            stream, lambda: g.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image), reps, flush) * 1e6
+        cnt = g.counters()
+        I, n_vis = int(cnt[0]), int(cnt[4])
+        t = table["gs_raster_bwd"] * 1e-6
+        alg = 24 * P + 48 * I + 80 * n_vis
         ach = alg / t / 1e9
-        return {"kernel": "k_integrate_tma", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                "traffic": None, "algorithmic_bytes": alg, "avg_launch_us": t * 1e6, "units": {"visible_blocks": V, "pixels": P}}
+        return {"kernel": "k_raster_bwd", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                "traffic": None, "algorithmic_bytes": alg, "avg_launch_us": t * 1e6,
+                "units": {"pixels": P, "isects": I, "visible_gaussians": n_vis, "gaussians": self.n_gauss},
+                "kernels_us": table, "tsdf_integrate": integrate}

@@ -75,6 +75,7 @@ int gsb_tsdf_process_frame_device(gsb_tsdf_t *e, const void *rgba_dev, const voi
 int gsb_tsdf_run_raycast(gsb_tsdf_t *e, const float *c2w, float fx, float fy, float cx, float cy);
 const void *gsb_tsdf_free_image_dev(gsb_tsdf_t *e);   /* GetFreeImage()->GetData(MEMORYDEVICE_CUDA): uchar4 [h*w]  */
 const void *gsb_tsdf_free_vertex_dev(gsb_tsdf_t *e);  /* GetFreeVertex(): float4 [h*w], xyz in voxel units, w=conf+1 */
+const void *gsb_tsdf_current_rgba_dev(gsb_tsdf_t *e); /* uchar4 [h*w]: the RGBA frame the last ProcessFrame consumed        */
 const void *gsb_tsdf_live_vertex_dev(gsb_tsdf_t *e);  /* GetLiveVertex()                                             */
 const void *gsb_tsdf_points_map_dev(gsb_tsdf_t *e);   /* trackingState->pointCloud->locations (metres, w=conf+1/-1)  */
 const void *gsb_tsdf_normals_map_dev(gsb_tsdf_t *e);  /* trackingState->pointCloud->colours                          */
@@ -163,6 +164,24 @@ int gsb_gs_loss(gsb_gs_t *e, double *loss);                               /* los
 /* SLAMPipeline::removeRedundantGs + prunePoints (remove_configs.low_opac_thres, small_scale_thres, large_scale_thres) */
 int gsb_gs_prune(gsb_gs_t *e, float min_opac, float min_scale, float max_scale);
 
+/* SLAMPipeline::initNewGaussians + SLAMGaussianModel::addGaussians (slam/slam_pipeline.cpp:450-526, slam/slam_gs_model.cpp:5-56) */
+typedef struct gsb_spawn_config
+{
+    float color_error_thres;      /* PIPE.color_error_thres (0.05)                        */
+    float depth_vis_min, depth_vis_max, alpha_vis_max;   /* PIPE.vis_configs (0, 5, 5)    */
+    float sample_ratio;           /* PIPE.new_gs_sample_ratio (0.25)                      */
+    float max_init_scale, min_init_scale, default_opacity;   /* MODEL (0.01, -1, 0.5)     */
+    unsigned seed;                /* sampling seed (the reference draws torch::randperm)  */
+} gsb_spawn_config_t;
+int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const float *c2w, float fx, float fy, float cx, float cy,
+                 const void *free_vertex_dev, float voxel_size, const float *depth_map_dev, const float *color_map_dev,
+                 const float *gt_rgb_dev);
+/* runRaycastByCam tensor glue (slam/slam_pipeline.cpp:386-403): GetFreeVertex()/GetFreeImage() -> depth_map, color_map, confidence */
+int gsb_gs_raycast_maps(gsb_gs_t *e, const void *free_vertex_dev, const void *free_image_dev, const float *c2w, float voxel_size,
+                        float *depth_map_dev, float *color_map_dev, float *conf_map_dev);
+/* Camera::image / Camera::depth (float) from the raw RGBA8 / int16-mm frame */
+int gsb_gs_frame_to_float(gsb_gs_t *e, const void *rgba_dev, const void *depth_mm_dev, float *rgb_dev, float *depth_dev);
+
 /* state read-back for parity tests (synchronises) */
 enum
 {
@@ -175,6 +194,9 @@ enum
     GSB_GS_GRAD_MEANS = 6, GSB_GS_GRAD_SCALES = 7, GSB_GS_GRAD_QUATS = 8, GSB_GS_GRAD_DC = 9, GSB_GS_GRAD_REST = 10, GSB_GS_GRAD_OPAC = 11
 };
 int gsb_gs_read(gsb_gs_t *e, int what, void *dst_host, size_t bytes);
+/* single stages on the camera / images of the last train step, for per-kernel timing: 0 projection+SH, 1 tile binning,
+ * 2 rasteriser forward (train), 3 rasteriser backward, 4 drop the backward work list (call last) */
+int gsb_gs_run_stage(gsb_gs_t *e, int stage);
 int gsb_gs_enable_grad_dump(gsb_gs_t *e, int on);   /* keep the parameter gradients of each train step for GSB_GS_GRAD_* */
 
 #ifdef __cplusplus
