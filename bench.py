@@ -38,6 +38,8 @@ def parse_args():
     ap.add_argument("--mode", default=None, choices=["train", "recon"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--timing-reps", type=int, default=20)
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per step for --impl reference (0 = auto)")
     return ap.parse_args()
 
@@ -271,7 +273,7 @@ def main():
     ms, launches, clocks = run_leg(True)
     stats = pipe.stats()
     psnr = eval_psnr(pipe, intr, poses, rgba, n_frames, dev) if mode == "train" else None
-    ms_e2e, _, _ = run_leg(False)
+    ms_e2e = run_leg(False)[0] if not args.no_e2e else float("nan")
     frames = args.steps * FRAMES_PER_STEP
     fps = frames / (ms * 1e-3)
     fps_e2e = frames / (ms_e2e * 1e-3)
@@ -280,7 +282,9 @@ def main():
     roofline = None
     if not args.no_kernel_timing and rank == 0:
         peak, peak_src = load_peaks()
-        roofline = pipe.time_dominant_kernel(stream, peak)
+        torch.cuda.nvtx.range_push("kernel_timing")   # ncu --nvtx --nvtx-include "kernel_timing/" captures steady-state launches
+        roofline = pipe.time_dominant_kernel(stream, peak, reps=args.timing_reps)
+        torch.cuda.nvtx.range_pop()
         roofline["peak_source"] = peak_src
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -51,7 +51,8 @@ enum
     CNT_OVERFLOW = 2, // bit 0: intersections exceeded isectCap, bit 1: backward items exceeded itemCap, bit 2: Gaussian capacity
     CNT_VISIBLE = 3,  // running count of Gaussians with radius > 0 (moved to CNT_VISIBLE_LAST by the binning pass)
     CNT_VISIBLE_LAST = 4,
-    CNT_SCRATCH = 5,  // prune / spawn scratch (3 ints)
+    CNT_SCRATCH = 5,  // prune / spawn scratch (2 ints)
+    CNT_BWD_CURSOR = 7, // work-item cursor of the rasteriser backward
     CNT_TOTAL = 8
 };
 
@@ -100,8 +101,8 @@ void project_sh_fwd(const ParamPtrs &p, const int *nDev, int nUpper, const CamPa
 void bin_tiles(const SplatRec *recs, const int *nDev, int nUpper, const Bins &bins, int tileW, int tileH, cudaStream_t st);
 // dbg: optional dump of the parameter gradients (same layout as the parameters); nullptr in production
 void bwd_params_adam(const ParamPtrs &p, const ParamPtrs &m, const ParamPtrs &v, unsigned char *touched, const AdamStep &step, const int *nDev,
-                     int nUpper, const CamParams &cam, const SplatRec *recs, const SplatGrad *grads, const ParamPtrs *dbg, int *counters,
-                     cudaStream_t st);
+                     int nUpper, const CamParams &cam, const SplatRec *recs, const SplatGrad *grads, float4 *aux /* [N*5] */,
+                     const ParamPtrs *dbg, int *counters, cudaStream_t st);
 void reduce_loss(const float *lossTile, int T, double scale, double *out, cudaStream_t st);
 // removeRedundantGs + prunePoints: stable compaction of parameters (Adam state is re-created by the next cycle)
 void prune(const ParamPtrs &p, const ParamPtrs &tmp, int *nDev, int nUpper, float minOpac, float minScale, float maxScale, int *scanTmp,

@@ -28,6 +28,7 @@ struct gsb_gs
     unsigned char *touched;
     SplatRec *recs;
     SplatGrad *grads;
+    float4 *aux;     // [cap*5] per-Gaussian SH basis / colour gradient / state flag between the two backward kernels
     Bins bins;
     float4 *v_out;
     float *v_depth;
@@ -130,6 +131,7 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     rc |= dev_alloc(e, &e->touched, (size_t)e->cap);
     rc |= dev_alloc(e, &e->recs, (size_t)e->cap);
     rc |= dev_alloc(e, &e->grads, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->aux, (size_t)e->cap * 5);
     rc |= dev_alloc(e, &e->nDev, 1);
     e->bins.isectCap = cfg->isect_capacity > 0 ? cfg->isect_capacity : (1 << 24);
     e->bins.itemCap = cfg->item_capacity > 0 ? cfg->item_capacity : (1 << 23);
@@ -376,8 +378,8 @@ extern "C" int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float 
     const double lr[6] = {(double)e->cfg.lr_means * e->cfg.scene_scale, e->cfg.lr_scales, e->cfg.lr_quats, e->cfg.lr_dc, e->cfg.lr_rest, e->cfg.lr_opac};
     for (int i = 0; i < 6; i++)
         s.step_size[i] = (float)(lr[i] / bc1);
-    bwd_params_adam(e->p, e->m, e->v, e->touched, s, e->nDev, e->nUpper, cam, e->recs, e->grads, e->haveDbg ? &e->dbg : nullptr, e->bins.counters,
-                    e->stream);
+    bwd_params_adam(e->p, e->m, e->v, e->touched, s, e->nDev, e->nUpper, cam, e->recs, e->grads, e->aux, e->haveDbg ? &e->dbg : nullptr,
+                    e->bins.counters, e->stream);
     GS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -506,7 +508,8 @@ extern "C" int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const flo
 
 // Single stages on the camera / images of the last gsb_gs_train_step, for per-kernel timing (bench.py roofline, ncu).
 // stage: 0 projection+SH (for backward), 1 tile binning, 2 rasteriser forward (train mode), 3 rasteriser backward,
-//        4 drop the backward work list (leaves the engine ready for the next train step).  Run 0,1,2 before 3; finish with 4.
+//        4 drop the backward work list (leaves the engine ready for the next train step), 5 parameter backward + Adam with a
+//        zero step size.  Stage 1 re-runs stage 0 first.  Run 1,2 before 3 and 5; finish with 4.
 extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
 {
     if (!e->haveLast)
@@ -518,10 +521,25 @@ extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
         GS_CUDA_OK(cudaMemsetAsync(e->bins.tileCount, 0, sizeof(int) * (e->T + 1), e->stream));
         project_sh_fwd(e->p, e->nDev, e->nUpper, e->lastCam, e->recs, e->grads, e->bins, e->tileW, e->tileH, true, e->stream);
         break;
-    case 1: bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream); break;
+    case 1: // binning consumes the tile counts, so it is always timed together with the projection that produces them
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.tileCount, 0, sizeof(int) * (e->T + 1), e->stream));
+        project_sh_fwd(e->p, e->nDev, e->nUpper, e->lastCam, e->recs, e->grads, e->bins, e->tileW, e->tileH, true, e->stream);
+        bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
+        break;
     case 2: raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, e->lastIo, e->stream); break;
     case 3: raster_bwd(e->recs, e->bins, e->W, e->H, e->lastIo, nullptr, e->grads, e->stream); break;
     case 4: GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream)); break;
+    case 5: // parameter backward + Adam with a zero step size (moments advance, parameters do not move)
+    {
+        AdamStep s;
+        s.a.beta1 = 0.9f, s.a.beta2 = 0.999f, s.a.one_m_beta1 = 0.1f, s.a.one_m_beta2 = 0.001f, s.a.sqrt_bc2 = 1.0f, s.a.eps = 1e-15f;
+        for (int i = 0; i < 6; i++)
+            s.step_size[i] = 0.f;
+        bwd_params_adam(e->p, e->m, e->v, e->touched, s, e->nDev, e->nUpper, e->lastCam, e->recs, e->grads, e->aux, nullptr, e->bins.counters,
+                        e->stream);
+        break;
+    }
     default: return gs_set_error(__FILE__, __LINE__, "bad stage id");
     }
     GS_CUDA_OK(cudaGetLastError());

@@ -72,6 +72,21 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
         o = project_one(mean, quat, scale, cam, nullptr);
     }
     const bool vis = o.radius > 0;
+    const unsigned full = 0xffffffffu;
+    const unsigned vm = __ballot_sync(full, vis);
+    // the 15x3 higher-order SH coefficients of the warp's 32 consecutive Gaussians are one contiguous 5,760-byte run: stage it in
+    // shared memory with coalesced loads; lanes then read their own row at stride 45 (odd -> conflict free)
+    __shared__ float sRest[4][32 * 45];
+    float *rest = sRest[threadIdx.x >> 5];
+    if (vm)
+    {
+        const int g0 = g - lane;
+        const int nRest = min(32, *nDev - g0) * 45;
+        const float *src = p.rest + (size_t)g0 * 45;
+        for (int i = lane; i < nRest; i += 32)
+            rest[i] = src[i];
+    }
+    __syncwarp();
     int nItems = 0;
     int bits = 0;
     float col[3] = {0.f, 0.f, 0.f};
@@ -84,7 +99,10 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
         ShBasis sb;
         sh_basis(dir, sb);
         float cl[48];
-        load_coeffs(p, g, cl);
+        cl[0] = p.dc[g * 3 + 0], cl[1] = p.dc[g * 3 + 1], cl[2] = p.dc[g * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < 45; i++)
+            cl[3 + i] = rest[lane * 45 + i];
 #pragma unroll
         for (int c = 0; c < 3; c++)
         {
@@ -111,8 +129,6 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
         }
     }
     // warp-aggregated reservation of backward work items and of the visible count (one atomic per warp)
-    const unsigned full = 0xffffffffu;
-    unsigned vm = __ballot_sync(full, vis);
     if (vm == 0)
     {
         if (inRange)
@@ -314,23 +330,48 @@ __device__ __forceinline__ void adam_one(float *p, float *m, float *v, size_t id
     p[idx] = pn, m[idx] = mo, v[idx] = vo;
 }
 
-__global__ void __launch_bounds__(128) k_bwd_params_adam(ParamPtrs p, ParamPtrs m, ParamPtrs v, unsigned char *touched, AdamStep step,
-                                                          const int *__restrict__ nDev, CamParams cam, const SplatRec *__restrict__ recs,
-                                                          const SplatGrad *__restrict__ grads, ParamPtrs dbg, int haveDbg, int *counters)
+// Parameter backward + Adam in two kernels.
+//  k_bwd_params: one lane per Gaussian (a warp owns 32 consecutive ones).  The 15x3 higher-order SH coefficients of those 32
+//     Gaussians are one contiguous 5,760-byte run: the warp stages it in shared memory with coalesced loads and every lane reads
+//     its own 45 coefficients at stride 45 (odd -> conflict free) for the SH VJP.  It applies Adam to the 14 "small" parameters
+//     (means, scales, quats, DC colour, opacity) and leaves, per Gaussian, the 15 SH basis values, the 3 colour gradients and a
+//     state flag in an 80-byte aux record.
+//  k_adam_rest: pure streaming pass over the higher-order SH coefficients and their two moments (76% of all parameter bytes):
+//     16-byte accesses, two per thread in flight, gradient = basis[k] * v_colour[c] rebuilt from the aux record.
+constexpr int ADAM_WARPS = 4;
+constexpr int AUX_FLOATS = 20; // basis[1..15], vcol[3], flag, pad
+__global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, ParamPtrs m, ParamPtrs v, unsigned char *touched, AdamStep step,
+                                                                   const int *__restrict__ nDev, CamParams cam,
+                                                                   const SplatRec *__restrict__ recs, const SplatGrad *__restrict__ grads,
+                                                                   float4 *__restrict__ aux, ParamPtrs dbg, int haveDbg, int *counters)
 {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0)
-    {
+    __shared__ float sRest[ADAM_WARPS][32 * 45];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g0 = (blockIdx.x * ADAM_WARPS + wid) * 32;
+    const int g = g0 + lane;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
         counters[CNT_ITEMS] = 0; // re-arm for the next projection
-    }
-    if (g >= *nDev)
+    const int N = *nDev;
+    if (g0 >= N)
         return;
-    float4 q0 = recs[g].q0;
+    const bool inRange = g < N;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inRange)
+        q0 = recs[g].q0;
     const int radius = __float_as_int(q0.w);
-    const bool vis = radius > 0;
-    const bool had = touched[g] != 0;
-    if (!vis && !had && !haveDbg)
-        return;
+    const bool vis = inRange && radius > 0;
+    const bool had = inRange && touched[g] != 0;
+    const unsigned full = 0xffffffffu;
+    const unsigned visMask = __ballot_sync(full, vis);
+    float *rest = sRest[wid];
+    if (visMask)
+    {
+        const int nRest4 = min(32, N - g0) * 45 / 4 + 1; // buffers are padded to a multiple of 128 Gaussians
+        const float4 *src = reinterpret_cast<const float4 *>(p.rest + (size_t)g0 * 45);
+        for (int i = lane; i < min(nRest4, 360); i += 32)
+            reinterpret_cast<float4 *>(rest)[i] = src[i];
+    }
+    __syncwarp();
     float gm[3] = {0.f, 0.f, 0.f}, gsc[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gdc[3] = {0.f, 0.f, 0.f}, gop = 0.f;
     float basis[16], vcol[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -354,7 +395,10 @@ __global__ void __launch_bounds__(128) k_bwd_params_adam(ParamPtrs p, ParamPtrs 
         ShBasis sb;
         sh_basis(dir, sb);
         float cl[48];
-        load_coeffs(p, g, cl);
+        cl[0] = p.dc[g * 3 + 0], cl[1] = p.dc[g * 3 + 1], cl[2] = p.dc[g * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < 45; i++)
+            cl[3 + i] = rest[lane * 45 + i];
         float vdir[3];
         sh_vjp(sb, cl, 3, vcol, basis, vdir);
         float vmean[3], vquat[4], vscale[3];
@@ -372,7 +416,20 @@ __global__ void __launch_bounds__(128) k_bwd_params_adam(ParamPtrs p, ParamPtrs 
         float o = q0.z;
         gop = sg.g0.z * o * (1.0f - o);
     }
-    if (haveDbg)
+    if (inRange)
+    {
+        const int flag = (vis ? 1 : 0) | (had ? 2 : 0);
+        float4 *a = aux + (size_t)g * (AUX_FLOATS / 4);
+        if (vis)
+        {
+            a[0] = make_float4(basis[1], basis[2], basis[3], basis[4]);
+            a[1] = make_float4(basis[5], basis[6], basis[7], basis[8]);
+            a[2] = make_float4(basis[9], basis[10], basis[11], basis[12]);
+            a[3] = make_float4(basis[13], basis[14], basis[15], vcol[0]);
+        }
+        a[4] = make_float4(vcol[1], vcol[2], __int_as_float(flag), 0.f);
+    }
+    if (haveDbg && inRange)
     {
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -383,30 +440,115 @@ __global__ void __launch_bounds__(128) k_bwd_params_adam(ParamPtrs p, ParamPtrs 
         dbg.opac[g] = gop;
         for (int e = 0; e < 45; e++)
             dbg.rest[(size_t)g * 45 + e] = basis[e / 3 + 1] * vcol[e % 3];
-        if (!vis && !had)
-            return;
     }
     // Adam: a Gaussian that never received a gradient in this optimiser cycle has m = v = 0 and a zero update, so it is
     // skipped exactly; its state is materialised on first touch.
-#pragma unroll
-    for (int i = 0; i < 3; i++)
+    if (vis || had)
     {
-        adam_one(p.means, m.means, v.means, (size_t)g * 3 + i, gm[i], had, step.a, step.step_size[0]);
-        adam_one(p.scales, m.scales, v.scales, (size_t)g * 3 + i, gsc[i], had, step.a, step.step_size[1]);
-        adam_one(p.dc, m.dc, v.dc, (size_t)g * 3 + i, gdc[i], had, step.a, step.step_size[3]);
-    }
+        // small parameter groups: 13 values per Gaussian; all loads are issued before the first store
+        float P13[13], M13[13], V13[13], G13[13];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-        adam_one(p.quats, m.quats, v.quats, (size_t)g * 4 + i, gq[i], had, step.a, step.step_size[2]);
-    adam_one(p.opac, m.opac, v.opac, (size_t)g, gop, had, step.a, step.step_size[5]);
-#pragma unroll 3
-    for (int e = 0; e < 45; e++)
-    {
-        int k = e / 3 + 1, c = e - (e / 3) * 3;
-        float ge = vis ? basis[k] * vcol[c] : 0.f;
-        adam_one(p.rest, m.rest, v.rest, (size_t)g * 45 + e, ge, had, step.a, step.step_size[4]);
+        for (int i = 0; i < 3; i++)
+        {
+            P13[i] = p.means[g * 3 + i], P13[3 + i] = p.scales[g * 3 + i], P13[6 + i] = p.dc[g * 3 + i];
+            G13[i] = gm[i], G13[3 + i] = gsc[i], G13[6 + i] = gdc[i];
+        }
+        {
+            float4 q4 = reinterpret_cast<const float4 *>(p.quats)[g];
+            P13[9] = q4.x, P13[10] = q4.y, P13[11] = q4.z, P13[12] = q4.w;
+            G13[9] = gq[0], G13[10] = gq[1], G13[11] = gq[2], G13[12] = gq[3];
+        }
+        float po = p.opac[g], mo = 0.f, vo = 0.f;
+#pragma unroll
+        for (int i = 0; i < 13; i++)
+            M13[i] = 0.f, V13[i] = 0.f;
+        if (had)
+        {
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+            {
+                M13[i] = m.means[g * 3 + i], M13[3 + i] = m.scales[g * 3 + i], M13[6 + i] = m.dc[g * 3 + i];
+                V13[i] = v.means[g * 3 + i], V13[3 + i] = v.scales[g * 3 + i], V13[6 + i] = v.dc[g * 3 + i];
+            }
+            float4 mq = reinterpret_cast<const float4 *>(m.quats)[g], vq = reinterpret_cast<const float4 *>(v.quats)[g];
+            M13[9] = mq.x, M13[10] = mq.y, M13[11] = mq.z, M13[12] = mq.w;
+            V13[9] = vq.x, V13[10] = vq.y, V13[11] = vq.z, V13[12] = vq.w;
+            mo = m.opac[g], vo = v.opac[g];
+        }
+#pragma unroll
+        for (int i = 0; i < 13; i++)
+        {
+            const float ss = i < 3 ? step.step_size[0] : (i < 6 ? step.step_size[1] : (i < 9 ? step.step_size[3] : step.step_size[2]));
+            P13[i] = adam_update(P13[i], G13[i], M13[i], V13[i], step.a, ss);
+        }
+        po = adam_update(po, gop, mo, vo, step.a, step.step_size[5]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            p.means[g * 3 + i] = P13[i], p.scales[g * 3 + i] = P13[3 + i], p.dc[g * 3 + i] = P13[6 + i];
+            m.means[g * 3 + i] = M13[i], m.scales[g * 3 + i] = M13[3 + i], m.dc[g * 3 + i] = M13[6 + i];
+            v.means[g * 3 + i] = V13[i], v.scales[g * 3 + i] = V13[3 + i], v.dc[g * 3 + i] = V13[6 + i];
+        }
+        reinterpret_cast<float4 *>(p.quats)[g] = make_float4(P13[9], P13[10], P13[11], P13[12]);
+        reinterpret_cast<float4 *>(m.quats)[g] = make_float4(M13[9], M13[10], M13[11], M13[12]);
+        reinterpret_cast<float4 *>(v.quats)[g] = make_float4(V13[9], V13[10], V13[11], V13[12]);
+        p.opac[g] = po, m.opac[g] = mo, v.opac[g] = vo;
+        touched[g] = 1;
     }
-    touched[g] = 1;
+}
+
+__device__ __forceinline__ void adam_rest4(float4 &P, float4 &M, float4 &V, int i4, int N, const float *__restrict__ aux, const AdamStep &step)
+{
+    float pv[4] = {P.x, P.y, P.z, P.w}, mv[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++)
+    {
+        const int i = i4 * 4 + c4;
+        const int gl = i / 45, e = i - gl * 45;
+        if (gl >= N)
+            continue;
+        const float *a = aux + (size_t)gl * AUX_FLOATS;
+        const int fl = __float_as_int(__ldg(a + 18));
+        if (fl == 0)
+            continue;
+        const int k = e / 3, c = e - k * 3; // basis index k + 1
+        const float ge = (fl & 1) ? __ldg(a + k) * __ldg(a + 15 + c) : 0.f;
+        float mo = (fl & 2) ? mv[c4] : 0.f, vo = (fl & 2) ? vv[c4] : 0.f;
+        pv[c4] = adam_update(pv[c4], ge, mo, vo, step.a, step.step_size[4]);
+        mv[c4] = mo, vv[c4] = vo;
+    }
+    P = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    M = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    V = make_float4(vv[0], vv[1], vv[2], vv[3]);
+}
+
+__global__ void __launch_bounds__(256) k_adam_rest(float4 *__restrict__ pR, float4 *__restrict__ mR, float4 *__restrict__ vR,
+                                                    const float *__restrict__ aux, const int *__restrict__ nDev, AdamStep step)
+{
+    const int N = *nDev;
+    const int total4 = (N * 45 + 3) / 4;
+    const int i4a = (blockIdx.x * 256 + threadIdx.x) * 2, i4b = i4a + 1;
+    if (i4a >= total4)
+        return;
+    // skip float4s whose (at most two) Gaussians are both inactive
+    const int ga0 = (i4a * 4) / 45, ga1 = min((i4a * 4 + 3) / 45, N - 1), gb1 = min((i4b * 4 + 3) / 45, N - 1);
+    const int fa = __float_as_int(__ldg(aux + (size_t)ga0 * AUX_FLOATS + 18)) | __float_as_int(__ldg(aux + (size_t)ga1 * AUX_FLOATS + 18));
+    const int fb = (i4b < total4) ? (__float_as_int(__ldg(aux + (size_t)ga1 * AUX_FLOATS + 18)) | __float_as_int(__ldg(aux + (size_t)gb1 * AUX_FLOATS + 18))) : 0;
+    float4 Pa, Ma, Va, Pb, Mb, Vb;
+    if (fa)
+        Pa = pR[i4a], Ma = mR[i4a], Va = vR[i4a];
+    if (fb)
+        Pb = pR[i4b], Mb = mR[i4b], Vb = vR[i4b];
+    if (fa)
+    {
+        adam_rest4(Pa, Ma, Va, i4a, N, aux, step);
+        pR[i4a] = Pa, mR[i4a] = Ma, vR[i4a] = Va;
+    }
+    if (fb)
+    {
+        adam_rest4(Pb, Mb, Vb, i4b, N, aux, step);
+        pR[i4b] = Pb, mR[i4b] = Mb, vR[i4b] = Vb;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_reduce_loss(const float *__restrict__ lossTile, int T, double scale, double *out)
@@ -556,14 +698,18 @@ void bin_tiles(const SplatRec *recs, const int *nDev, int nUpper, const Bins &bi
 }
 
 void bwd_params_adam(const ParamPtrs &p, const ParamPtrs &m, const ParamPtrs &v, unsigned char *touched, const AdamStep &step, const int *nDev,
-                     int nUpper, const CamParams &cam, const SplatRec *recs, const SplatGrad *grads, const ParamPtrs *dbg, int *counters,
-                     cudaStream_t st)
+                     int nUpper, const CamParams &cam, const SplatRec *recs, const SplatGrad *grads, float4 *aux, const ParamPtrs *dbg,
+                     int *counters, cudaStream_t st)
 {
     if (nUpper <= 0)
         return;
-    GS_COUNT_LAUNCHES(1);
+    GS_COUNT_LAUNCHES(2);
     ParamPtrs d = dbg ? *dbg : p;
-    k_bwd_params_adam<<<cdiv(nUpper, 128), 128, 0, st>>>(p, m, v, touched, step, nDev, cam, recs, grads, d, dbg ? 1 : 0, counters);
+    k_bwd_params<<<cdiv(nUpper, ADAM_WARPS * 32), ADAM_WARPS * 32, 0, st>>>(p, m, v, touched, step, nDev, cam, recs, grads, aux, d, dbg ? 1 : 0,
+                                                                            counters);
+    const long long total4 = ((long long)nUpper * 45 + 3) / 4;
+    k_adam_rest<<<(int)((total4 + 511) / 512), 256, 0, st>>>(reinterpret_cast<float4 *>(p.rest), reinterpret_cast<float4 *>(m.rest),
+                                                              reinterpret_cast<float4 *>(v.rest), reinterpret_cast<const float *>(aux), nDev, step);
 }
 
 void reduce_loss(const float *lossTile, int T, double scale, double *out, cudaStream_t st)

@@ -138,19 +138,30 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__ recs, const int2 *__restrict__ items,
-                                                     const int *__restrict__ counters, int itemCap, int W, int H,
-                                                     const float *__restrict__ refDepth, int clampRef, float deltaDepth,
+__global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__ recs, const int2 *__restrict__ items, int *counters, int itemCap,
+                                                     int W, int H, const float *__restrict__ refDepth, int clampRef, float deltaDepth,
                                                      const float4 *__restrict__ v_out, const float *__restrict__ v_depthImg,
                                                      SplatGrad *__restrict__ grads)
 {
     const int lane = threadIdx.x & 31;
-    const int warpsPerBlock = blockDim.x >> 5;
-    const int nWarps = gridDim.x * warpsPerBlock;
     const int nItems = min(counters[CNT_ITEMS], itemCap);
-    for (int it = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); it < nItems; it += nWarps)
+    // dynamic distribution of work items over the resident warps: items differ by up to 64x in cost
+    int *cursor = counters + CNT_BWD_CURSOR;
+    constexpr int GRAB = 8; // consecutive items per cursor bump (same-address atomics are the scarce resource)
+    int it = 0, itEnd = 0;
+    for (;;)
     {
+        if (it >= itEnd)
+        {
+            if (lane == 0)
+                it = atomicAdd(cursor, GRAB);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= nItems)
+                break;
+            itEnd = min(it + GRAB, nItems);
+        }
         const int2 item = __ldg(&items[it]);
+        it++;
         const int g = item.x;
         const float4 q0 = __ldg(&recs[g].q0), q1 = __ldg(&recs[g].q1), q2 = __ldg(&recs[g].q2);
         const int radius = __float_as_int(q0.w);
@@ -163,43 +174,62 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
         const int g0 = item.y * BWD_GROUPS_PER_ITEM;
         const int g1 = min(g0 + BWD_GROUPS_PER_ITEM, groups);
         float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, vca = 0.f, vcb = 0.f, vcc = 0.f, vx = 0.f, vy = 0.f, vo = 0.f;
-        for (int grp = g0; grp < g1; grp++)
+        // two groups (64 box pixels) per step: their image reads are issued together, before either is consumed
+        for (int grp = g0; grp < g1; grp += 2)
         {
-            const int id = grp * 32 + lane;
-            const int row = (int)(((float)id + 0.5f) * inv_bw); // exact for id < 2^16, bw <= 200
-            const int col = id - row * bw;
-            const int j = x_min + 1 + col, i = y_min + 1 + row;
-            if (i < 0 || j < 0 || i >= H || j >= W || i > y_max)
-                continue;
-            const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-            const float dx = q0.x - px, dy = q0.y - py;
-            const float sigma = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
-            const float vis = __expf(-sigma);
-            const float alpha = fminf(0.999f, opac * vis);
-            if (sigma < 0.f || alpha < 1.f / 255.f)
-                continue;
-            const int pix = i * W + j;
-            float rd = __ldg(&refDepth[pix]);
-            if (clampRef && rd < 0.01f)
-                rd = 1000.0f;
-            if (q1.w > rd + deltaDepth)
-                continue;
-            const float4 vo4 = __ldg(&v_out[pix]);
-            const float vdp = v_depthImg ? __ldg(&v_depthImg[pix]) : 0.f;
-            vr += alpha * vo4.x;
-            vg += alpha * vo4.y;
-            vb += alpha * vo4.z;
-            vd += alpha * vdp;
-            float v_alpha = q2.x * vo4.x + q2.y * vo4.y + q2.z * vo4.z + q1.w * vdp + vo4.w;
-            if (opac * vis <= 0.999f)
+            float dxs[2], dys[2], viss[2], alphas[2], rds[2], vdps[2];
+            float4 vos[2];
+            bool oks[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++)
             {
-                const float v_sigma = -opac * vis * v_alpha;
-                vca += 0.5f * v_sigma * dx * dx;
-                vcb += v_sigma * dx * dy;
-                vcc += 0.5f * v_sigma * dy * dy;
-                vx += v_sigma * (q1.x * dx + q1.y * dy);
-                vy += v_sigma * (q1.y * dx + q1.z * dy);
-                vo += vis * v_alpha;
+                const int id = (grp + u) * 32 + lane;
+                const int row = (int)(((float)id + 0.5f) * inv_bw); // exact for id < 2^16, bw <= 200
+                const int col = id - row * bw;
+                const int j = x_min + 1 + col, i = y_min + 1 + row;
+                bool ok = (grp + u < g1) && !(i < 0 || j < 0 || i >= H || j >= W || i > y_max);
+                const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+                const float dx = q0.x - px, dy = q0.y - py;
+                const float sigma = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
+                const float vis = __expf(-sigma);
+                const float alpha = fminf(0.999f, opac * vis);
+                ok = ok && !(sigma < 0.f || alpha < 1.f / 255.f);
+                dxs[u] = dx, dys[u] = dy, viss[u] = vis, alphas[u] = alpha, oks[u] = ok;
+                rds[u] = 0.f, vdps[u] = 0.f, vos[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok)
+                {
+                    const int pix = i * W + j;
+                    rds[u] = __ldg(&refDepth[pix]);
+                    vos[u] = __ldg(&v_out[pix]);
+                    if (v_depthImg)
+                        vdps[u] = __ldg(&v_depthImg[pix]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+            {
+                float rd = rds[u];
+                if (clampRef && rd < 0.01f)
+                    rd = 1000.0f;
+                if (!oks[u] || q1.w > rd + deltaDepth)
+                    continue;
+                const float alpha = alphas[u], vis = viss[u], dx = dxs[u], dy = dys[u], vdp = vdps[u];
+                const float4 vo4 = vos[u];
+                vr += alpha * vo4.x;
+                vg += alpha * vo4.y;
+                vb += alpha * vo4.z;
+                vd += alpha * vdp;
+                const float v_alpha = q2.x * vo4.x + q2.y * vo4.y + q2.z * vo4.z + q1.w * vdp + vo4.w;
+                if (opac * vis <= 0.999f)
+                {
+                    const float v_sigma = -opac * vis * v_alpha;
+                    vca += 0.5f * v_sigma * dx * dx;
+                    vcb += v_sigma * dx * dy;
+                    vcc += 0.5f * v_sigma * dy * dy;
+                    vx += v_sigma * (q1.x * dx + q1.y * dy);
+                    vy += v_sigma * (q1.y * dx + q1.z * dy);
+                    vo += vis * v_alpha;
+                }
             }
         }
 #pragma unroll
@@ -263,6 +293,7 @@ void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, 
 void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth, SplatGrad *grads, cudaStream_t st)
 {
     GS_COUNT_LAUNCHES(1);
+    cudaMemsetAsync(bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), st);
     k_raster_bwd<<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, H, io.refDepth, io.clampRef, io.deltaDepth, io.v_out,
                                           v_depth, grads);
 }

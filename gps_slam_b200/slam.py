@@ -304,8 +304,15 @@ class SlamPipeline:
         with torch.cuda.stream(stream):
             g.initOptimizers()
             g.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image)
-        for name, st in (("gs_project_sh", 0), ("gs_bin_tiles(3 kernels)", 1), ("gs_raster_fwd_train", 2), ("gs_raster_bwd", 3)):
+        for name, st in (("gs_project_sh", 0), ("gs_project_sh+bin_tiles(4 kernels)", 1), ("gs_raster_fwd_train", 2), ("gs_raster_bwd", 3)):
             table[name] = self._time(stream, lambda st=st: g.run_stage(st), reps, flush) * 1e6
+        with torch.cuda.stream(stream):
+            g.run_stage(3)   # stage 5 clears the work list, so re-arm it each time: time 3+5 and subtract
+        def bwd_and_params():
+            g.run_stage(1)
+            g.run_stage(5)
+        t15 = self._time(stream, bwd_and_params, reps, flush) * 1e6
+        table["gs_bwd_params+adam_rest(2 kernels)"] = t15 - table["gs_project_sh+bin_tiles(4 kernels)"]
         with torch.cuda.stream(stream):
             g.run_stage(4)
         table["gs_train_step(7 kernels, no flush)"] = self._time(

@@ -195,7 +195,8 @@ enum
 };
 int gsb_gs_read(gsb_gs_t *e, int what, void *dst_host, size_t bytes);
 /* single stages on the camera / images of the last train step, for per-kernel timing: 0 projection+SH, 1 tile binning,
- * 2 rasteriser forward (train), 3 rasteriser backward, 4 drop the backward work list (call last) */
+ * (1 re-runs 0), 2 rasteriser forward (train), 3 rasteriser backward, 4 drop the backward work list (call last),
+ * 5 parameter backward + Adam with a zero step size (consumes the work list) */
 int gsb_gs_run_stage(gsb_gs_t *e, int stage);
 int gsb_gs_enable_grad_dump(gsb_gs_t *e, int on);   /* keep the parameter gradients of each train step for GSB_GS_GRAD_* */
 

@@ -2,8 +2,10 @@
 REFERENCE's own InfiniTAM CPU engine (built by oracle/itm_ref/Makefile from /root/reference).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
 """
+import contextlib
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -11,6 +13,25 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HASH_ENTRY = np.dtype([("pos", "<i2", 3), ("pad", "<i2"), ("offset", "<i4"), ("ptr", "<i4")])
 VOXEL = np.dtype([("sdf", "<i2"), ("w_depth", "u1"), ("clr", "u1", 3), ("w_color", "u1"), ("pad", "u1")])
 assert HASH_ENTRY.itemsize == 16 and VOXEL.itemsize == 8
+
+
+@contextlib.contextmanager
+def _quiet_stdout():
+    """the reference prints its settings with printf; keep them off our stdout (bench.py prints exactly one JSON line)"""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    null = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(null, 1)
+        yield
+    finally:
+        try:
+            C.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(saved, 1)
+        os.close(null)
+        os.close(saved)
 
 
 def lib_path(kind="exact"):
@@ -52,8 +73,9 @@ class ItmRef:
                      "tracker_result", "frames_processed"):
             getattr(L, "itmref_" + name).argtypes = [C.c_void_p]
         self.w, self.h = intr["width"], intr["height"]
-        self.h_ = L.itmref_create(self.w, self.h, intr["fx"], intr["fy"], intr["cx"], intr["cy"],
-                                  voxel, mu, vfmin, vfmax, tracker, threads)
+        with _quiet_stdout():
+            self.h_ = L.itmref_create(self.w, self.h, intr["fx"], intr["fy"], intr["cx"], intr["cy"],
+                                      voxel, mu, vfmin, vfmax, tracker, threads)
         self.E = L.itmref_num_hash_entries(self.h_)
         self.nblocks = L.itmref_num_blocks(self.h_)
 
