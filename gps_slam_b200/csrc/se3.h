@@ -9,10 +9,16 @@
 
 #include "common.cuh"
 
+#ifdef __CUDACC__
+#define SE3_HD __host__ __device__
+#else
+#define SE3_HD
+#endif
+
 namespace se3
 {
 
-inline bool inverse(const Mat4 &A, Mat4 &out)
+SE3_HD inline bool inverse(const Mat4 &A, Mat4 &out)
 {
     // cofactor expansion on the transposed source, 2x2 products shared pairwise
     float t[12], s[16], det;
@@ -62,7 +68,7 @@ inline bool inverse(const Mat4 &A, Mat4 &out)
 }
 
 // r = a * b with the reference's accumulate-from-zero order
-inline Mat4 mul(const Mat4 &a, const Mat4 &b)
+SE3_HD inline Mat4 mul(const Mat4 &a, const Mat4 &b)
 {
     Mat4 r;
     for (int i = 0; i < 16; i++)
@@ -79,21 +85,21 @@ struct Pose
     float p[6]; // tx ty tz rx ry rz
     Mat4 M;     // world -> camera
 
-    Pose() { set_params(0, 0, 0, 0, 0, 0); }
+    SE3_HD Pose() { set_params(0, 0, 0, 0, 0, 0); }
 
-    void set_params(float tx, float ty, float tz, float rx, float ry, float rz)
+    SE3_HD void set_params(float tx, float ty, float tz, float rx, float ry, float rz)
     {
         p[0] = tx, p[1] = ty, p[2] = tz, p[3] = rx, p[4] = ry, p[5] = rz;
         matrix_from_params();
     }
 
-    static void cross3(const float *a, const float *b, float *c)
+    SE3_HD static void cross3(const float *a, const float *b, float *c)
     {
         c[0] = a[1] * b[2] - a[2] * b[1];
         c[1] = a[2] * b[0] - a[0] * b[2];
         c[2] = a[0] * b[1] - a[1] * b[0];
     }
-    static float dot3(const float *a, const float *b)
+    SE3_HD static float dot3(const float *a, const float *b)
     {
         float r = 0;
         for (int i = 0; i < 3; i++)
@@ -102,7 +108,7 @@ struct Pose
     }
 
     // exponential map (Rodrigues with Taylor branches)
-    void matrix_from_params()
+    SE3_HD void matrix_from_params()
     {
         const float one_6th = 1.0f / 6.0f, one_20th = 1.0f / 20.0f;
         float w[3] = {p[3], p[4], p[5]}, t[3] = {p[0], p[1], p[2]};
@@ -160,7 +166,7 @@ struct Pose
     }
 
     // logarithm map
-    void params_from_matrix()
+    SE3_HD void params_from_matrix()
     {
         float R[9], T[3];
         for (int c = 0; c < 3; c++)
@@ -244,23 +250,23 @@ struct Pose
         p[0] = rt[0], p[1] = rt[1], p[2] = rt[2];
     }
 
-    void set_M(const Mat4 &m)
+    SE3_HD void set_M(const Mat4 &m)
     {
         M = m;
         params_from_matrix();
     }
-    void set_invM(const Mat4 &invM)
+    SE3_HD void set_invM(const Mat4 &invM)
     {
         inverse(invM, M);
         params_from_matrix();
     }
-    Mat4 get_invM() const
+    SE3_HD Mat4 get_invM() const
     {
         Mat4 r;
         inverse(M, r);
         return r;
     }
-    void coerce()
+    SE3_HD void coerce()
     {
         params_from_matrix();
         matrix_from_params();

@@ -364,3 +364,57 @@ extern "C" int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage)
     E_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ---- C. ICP tracker access (parity / diagnostics)
+extern "C" int gsb_tsdf_icp_eval(gsb_tsdf_t *e, int level, const float *approx_invM, int *n_valid, float *f, float *nabla6, float *hessian36)
+{
+    if (!e || !e->tracker)
+        return gs_set_error(__FILE__, __LINE__, "engine was created without a tracker");
+    if (!e->haveFrame)
+        return gs_set_error(__FILE__, __LINE__, "icp_eval needs a processed frame");
+    Mat4 inv;
+    memcpy(inv.m, approx_invM, 64);
+    return icp::icp_eval(e->tracker, e->depth_f, e->pointsMap, e->normalsMap, e->cam.fx, e->cam.fy, e->cam.cx, e->cam.cy, e->pose_pointCloud.M,
+                         e->trackingFrames, level, inv, n_valid, f, nabla6, hessian36, e->stream);
+}
+extern "C" int gsb_tsdf_set_tracking_frames(gsb_tsdf_t *e, int n)
+{
+    e->trackingFrames = n;
+    return 0;
+}
+extern "C" int gsb_tsdf_tracker_result(gsb_tsdf_t *e, int *result, float *score, int *iterations)
+{
+    if (!e || !e->tracker)
+        return gs_set_error(__FILE__, __LINE__, "engine was created without a tracker");
+    icp::tracker_result(e->tracker, result, score, iterations);
+    return 0;
+}
+extern "C" int gsb_tsdf_depth_level(gsb_tsdf_t *e, int level, float *dst_host, int *w, int *h)
+{
+    if (!e || !e->tracker)
+        return gs_set_error(__FILE__, __LINE__, "engine was created without a tracker");
+    const float *p = icp::level_depth(e->tracker, level, w, h);
+    if (level == 0)
+        p = e->depth_f;
+    if (!p)
+        return gs_set_error(__FILE__, __LINE__, "bad pyramid level");
+    if (dst_host)
+    {
+        E_CUDA(cudaMemcpyAsync(dst_host, p, sizeof(float) * (size_t)(*w) * (*h), cudaMemcpyDeviceToHost, e->stream));
+        E_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+// trackingState->pose_d->SetInvM(invM); Coerce()  -- initial pose when tracking is on (the reference starts from identity)
+extern "C" int gsb_tsdf_set_pose(gsb_tsdf_t *e, const float *invM)
+{
+    if (!e || !invM)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    Mat4 m;
+    memcpy(m.m, invM, 64);
+    e->pose_d.set_invM(m);
+    e->pose_d.coerce();
+    refresh_camera(e);
+    return 0;
+}

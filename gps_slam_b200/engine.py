@@ -85,12 +85,17 @@ def load_library():
         f.argtypes = [C.c_void_p]
         f.restype = C.c_void_p
     L.gsb_tsdf_get_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsb_tsdf_set_pose.argtypes = [C.c_void_p, C.c_void_p]
     L.gsb_tsdf_voxel_size.argtypes = [C.c_void_p]
     L.gsb_tsdf_voxel_size.restype = C.c_float
     L.gsb_tsdf_frames_processed.argtypes = [C.c_void_p]
     L.gsb_tsdf_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.gsb_tsdf_counter.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.gsb_tsdf_run_stage.argtypes = [C.c_void_p, C.c_int]
+    L.gsb_tsdf_icp_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+    L.gsb_tsdf_set_tracking_frames.argtypes = [C.c_void_p, C.c_int]
+    L.gsb_tsdf_tracker_result.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.gsb_tsdf_depth_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     # ---- section A: Gaussian model
     vp, fl = C.c_void_p, C.c_float
     L.gsb_gs_default_config.argtypes = [C.POINTER(GsConfig)]
@@ -206,6 +211,32 @@ class TsdfEngine:
         iM = np.zeros(16, np.float32)
         _check(self.L.gsb_tsdf_get_pose(self.h_, _ptr(M), _ptr(iM)))
         return M, iM
+
+    def icp_eval(self, level, approx_invM16):
+        a = np.ascontiguousarray(approx_invM16, dtype=np.float32)
+        n, f = C.c_int(0), C.c_float(0)
+        g, H = np.zeros(6, np.float32), np.zeros(36, np.float32)
+        _check(self.L.gsb_tsdf_icp_eval(self.h_, level, _ptr(a), C.byref(n), C.byref(f), _ptr(g), _ptr(H)))
+        return n.value, f.value, g, H
+
+    def set_tracking_frames(self, n):
+        _check(self.L.gsb_tsdf_set_tracking_frames(self.h_, n))
+
+    def tracker_result(self):
+        r, s, it = C.c_int(0), C.c_float(0), C.c_int(0)
+        _check(self.L.gsb_tsdf_tracker_result(self.h_, C.byref(r), C.byref(s), C.byref(it)))
+        return r.value, s.value, it.value
+
+    def depth_level(self, level):
+        w, h = C.c_int(0), C.c_int(0)
+        _check(self.L.gsb_tsdf_depth_level(self.h_, level, None, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.float32)
+        _check(self.L.gsb_tsdf_depth_level(self.h_, level, _ptr(out), C.byref(w), C.byref(h)))
+        return out
+
+    def set_pose(self, invM16):
+        a = np.ascontiguousarray(invM16, dtype=np.float32)
+        _check(self.L.gsb_tsdf_set_pose(self.h_, _ptr(a)))
 
     def resetAll(self):
         _check(self.L.gsb_tsdf_reset(self.h_))

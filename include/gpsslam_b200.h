@@ -82,6 +82,7 @@ const void *gsb_tsdf_normals_map_dev(gsb_tsdf_t *e);  /* trackingState->pointClo
 
 /* GetTrackingState()->pose_d: M = GetM() (world->camera), invM = GetInvM() */
 int gsb_tsdf_get_pose(gsb_tsdf_t *e, float *M, float *invM);
+int gsb_tsdf_set_pose(gsb_tsdf_t *e, const float *invM);          /* pose_d->SetInvM(invM); Coerce() */
 float gsb_tsdf_voxel_size(gsb_tsdf_t *e);
 int gsb_tsdf_frames_processed(gsb_tsdf_t *e);
 
@@ -108,6 +109,21 @@ int gsb_tsdf_counter(gsb_tsdf_t *e, int which, int *value);
 /* Single stages on the current frame / pose, for profiling and stage-level parity.
  * stage: 0 allocate (B1-B4), 1 integrate (B5), 2 expected depth (B6), 3 raycast (B7), 4 ICP maps (B8) */
 int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage);
+
+/* ===================================================================================================
+ * C.  ICP tracker  -- replaces ITMExtendedTracker (tracker == 1, the reference's compiled-in default) and ITMDepthTracker
+ *     (tracker == 2) (reference InfiniTAM/ITMLib/Trackers/Interface/ITMExtendedTracker.cpp:470-665, ITMDepthTracker.cpp:233-298).
+ *     Tracking itself runs inside gsb_tsdf_process_frame (ITMTrackingController::Track); these calls expose its pieces.
+ * =================================================================================================== */
+/* one evaluation of the ICP normal equations at pyramid `level` for the camera->world estimate approx_invM (16 floats,
+ * column-major) against the current raycast maps: ComputeGandH_Depth (extended: f is the un-normalised sum) / ComputeGandH
+ * (icp: f / n, or 1e5 when n <= 100).  hessian36 uses the reference's layout hessian[r + c*6]. Synchronises. */
+int gsb_tsdf_icp_eval(gsb_tsdf_t *e, int level, const float *approx_invM, int *n_valid, float *f, float *nabla6, float *hessian36);
+int gsb_tsdf_set_tracking_frames(gsb_tsdf_t *e, int n);          /* ITMTrackingState::framesProcessed (weights switch on at >= 100) */
+/* trackerResult of the last frame: 0 TRACKING_FAILED, 1 TRACKING_POOR, 2 TRACKING_GOOD; trackerScore; LM iterations run */
+int gsb_tsdf_tracker_result(gsb_tsdf_t *e, int *result, float *score, int *iterations);
+/* depth pyramid level after PrepareForEvaluation (level 0 = the float depth); dst_host may be NULL to query the size */
+int gsb_tsdf_depth_level(gsb_tsdf_t *e, int level, float *dst_host, int *w, int *h);
 
 /* ===================================================================================================
  * A.  Gaussian model  -- replaces RawGaussianModel / SLAMGaussianModel with render_method == "ges"

@@ -1,0 +1,105 @@
+"""GPU parity of the ICP tracker against the REFERENCE's own CPU trackers
+(ITMExtendedTracker_CPU / ITMDepthTracker_CPU inside oracle/_ref/libitm_ref_exact.so).
+
+  * C1 depth pyramid: bit-exact;
+  * C2/C3 one evaluation of the normal equations at every level for perturbed poses: the number of valid points is exact
+    (per-point math is bit-identical), f / g / H agree to 1e-3 of the largest entry (fp32 summation order: the CPU adds 10^5-10^6
+    terms one by one in raster order, the GPU sums in a fixed tree, which is the more accurate of the two);
+  * C4 tracked pose over a sequence: extended tracker (the reference's compiled-in default) within 2e-4 (matrix entries: metres /
+    unit rotation entries) of the reference's tracked pose; the icp flavour stops after 2-10 loosely converged iterations per
+    level (minstep 1e-3), so a single accept/reject decision that flips on the last bit of f moves the result by ~1e-3: its
+    bound is 3e-3.  Both stay within 3 mm / 0.1 degree of ground truth.
+"""
+import numpy as np
+import pytest
+
+from gps_slam_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def perturb(c2w_col, rng, rot=0.004, trans=0.004):
+    M = c2w_col.reshape(4, 4).T.astype(np.float64)   # row-major
+    w = rng.uniform(-rot, rot, 3)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    R = np.eye(3) + K + 0.5 * K @ K
+    D = np.eye(4)
+    D[:3, :3] = R
+    D[:3, 3] = rng.uniform(-trans, trans, 3)
+    return np.ascontiguousarray((D @ M).T.astype(np.float32)).reshape(16)
+
+
+def make_pair(intr, tracker):
+    from gps_slam_b200.engine import TsdfEngine
+    from oracle.itm_ref import ItmRef
+    return TsdfEngine(intr, tracker=tracker), ItmRef(intr, tracker=tracker, threads=1, kind="exact")
+
+
+@pytest.mark.parametrize("tracker", [1, 2])
+def test_pyramid_and_single_evaluations(engine_lib, tracker):
+    intr = syn.intrinsics("replica", 0.5)
+    poses, frames = syn.sequence(2, intr)
+    eng, ref = make_pair(intr, tracker)
+    try:
+        c0 = syn.c2w_to_colmajor(poses[0])
+        eng.set_pose(c0)
+        ref.set_pose_invM(c0)
+        rgba, d = frames[0][0].numpy(), frames[0][1].numpy()
+        eng.ProcessFrame(rgba, d, None)
+        ref.process_frame(rgba, d, None)
+        assert np.array_equal(eng.points_map().view(np.uint32), ref.points_map().view(np.uint32))
+        rng = np.random.RandomState(3)
+        n_levels = 4 if tracker == 1 else 5
+        for level in range(n_levels):
+            for trial in range(2):
+                inv = perturb(c0, rng) if trial else c0
+                n_r, f_r, g_r, H_r = ref.icp_eval(level, inv)
+                n_g, f_g, g_g, H_g = eng.icp_eval(level, inv)
+                if level > 0:
+                    assert np.array_equal(eng.depth_level(level).view(np.uint32), ref.depth_level(level).view(np.uint32)), "pyramid level %d" % level
+                assert n_g == n_r, "level %d: valid points %d vs %d" % (level, n_g, n_r)
+                assert n_r > 100
+                assert abs(f_g - f_r) <= 1e-3 * abs(f_r) + 1e-12, (level, f_g, f_r)
+                assert np.abs(g_g - g_r).max() <= 1e-3 * np.abs(g_r).max() + 1e-9, (level, g_g, g_r)
+                assert np.abs(H_g - H_r).max() <= 1e-3 * np.abs(H_r).max(), (level, np.abs(H_g - H_r).max(), np.abs(H_r).max())
+        if tracker == 1:
+            # confidence weights (useWeights) switch on once 100 frames have been tracked
+            eng.set_tracking_frames(150)
+            ref.set_tracking_frames(150)
+            n_r, f_r, g_r, H_r = ref.icp_eval(0, c0)
+            n_g, f_g, g_g, H_g = eng.icp_eval(0, c0)
+            assert n_g == n_r
+            assert np.abs(H_g - H_r).max() <= 1e-3 * np.abs(H_r).max() + 1e-12
+    finally:
+        eng.close()
+        ref.close()
+
+
+@pytest.mark.parametrize("tracker,n_frames", [(1, 12), (2, 8)])
+def test_tracked_sequence(engine_lib, tracker, n_frames):
+    intr = syn.intrinsics("replica", 0.5)
+    poses, frames = syn.sequence(n_frames, intr)
+    eng, ref = make_pair(intr, tracker)
+    try:
+        c0 = syn.c2w_to_colmajor(poses[0])
+        eng.set_pose(c0)
+        ref.set_pose_invM(c0)
+        for i in range(n_frames):
+            rgba, d = frames[i][0].numpy(), frames[i][1].numpy()
+            eng.ProcessFrame(rgba, d, None)
+            ref.process_frame(rgba, d, None)
+            ours = eng.pose()[1].reshape(4, 4).T
+            theirs = ref.pose()[1].reshape(4, 4).T
+            gt = poses[i]
+            tol = 2e-4 if tracker == 1 else 3e-3
+            assert np.abs(ours - theirs).max() < tol, "frame %d: tracked pose differs from the reference by %g" % (i, np.abs(ours - theirs).max())
+            assert np.linalg.norm(ours[:3, 3] - gt[:3, 3]) < 3e-3, "frame %d drift %g m" % (i, np.linalg.norm(ours[:3, 3] - gt[:3, 3]))
+            cosang = (np.trace(ours[:3, :3].T @ gt[:3, :3].astype(np.float64)) - 1) / 2
+            assert np.degrees(np.arccos(np.clip(cosang, -1, 1))) < 0.1
+            if i > 0:
+                res, score, iters = eng.tracker_result()
+                assert iters > 0 and np.isfinite(score)
+                assert res == ref.tracker_result() or tracker == 2, "tracking quality %d vs %d" % (res, ref.tracker_result())
+    finally:
+        eng.close()
+        ref.close()
