@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=None, choices=["train", "recon"])
+    ap.add_argument("--track", type=int, default=0, help="0: ground-truth poses (use_gt_pose=true, office0 config); 1: extended ICP tracker; 2: icp")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
@@ -231,7 +232,8 @@ def main():
     rgba_h = torch.empty(rgba.shape, dtype=rgba.dtype, pin_memory=True).copy_(rgba)
     depth_h = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True).copy_(depth)
     stream = torch.cuda.Stream(device=dev)
-    pipe = slam.SlamPipeline(intr, mode=mode, device=local, stream=stream, rank=rank, world=world)
+    pipe = slam.SlamPipeline(intr, mode=mode, device=local, stream=stream, rank=rank, world=world, use_gt_pose=args.track == 0,
+                             tracker=args.track or 1)
 
     def barrier():
         if world > 1:
@@ -295,7 +297,9 @@ def main():
             "metric": "slam_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": pipe.scaling(), "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": slam.workload_name(mode), "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
+            "config": dict({"workload": slam.workload_name(mode) + ("" if args.track == 0 else ", online ICP tracking (use_gt_pose=false)"),
+                            "parallelism": "single GPU" if world == 1 else "Gaussians sharded by spatial block over %d GPUs, one [H,W,5] "
+                                           "all-reduce per optimiser iteration; TSDF replicated" % world, "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
                             "l2": "no explicit flush: every frame is new input (4.9 MB) and each step streams the visible voxel "
                                   "blocks 10x (V x 8 KB per frame), working set > 126 MB L2", "quality": psnr}, **stats),
             "clocks": clocks, "gpu_launches": int(launches),

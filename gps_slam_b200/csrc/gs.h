@@ -128,6 +128,7 @@ void staged_adam(int n, float *p, const float *g, float *m, float *v, const Adam
 void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
 void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth /* nullable [H,W] */,
                 SplatGrad *grads, cudaStream_t st);
+void composite(int mode, const float *acc5 /* [P*4] render then [P] alphas */, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
 void pack_v_out(int P, const float *v_render4, const float *v_alphas, float4 *v_out, float *v_depth, cudaStream_t st);
 
 } // namespace gs

@@ -333,6 +333,22 @@ static RasterIO make_io(const gsb_gs *e, const float *ref_depth, const float *ba
     return io;
 }
 
+// torch::optim::Adam scalars for the current step; the step count is per optimiser and identical for the 6 of them
+static AdamStep make_adam_step(const gsb_gs *e)
+{
+    const double b1 = (double)0.9f, b2 = (double)0.999f; // float betas widened to double (src/raw_gs_model.cpp:662-663)
+    const double bc1 = 1.0 - pow(b1, e->adamStep), bc2 = 1.0 - pow(b2, e->adamStep);
+    AdamStep s;
+    s.a.beta1 = (float)b1, s.a.beta2 = (float)b2;
+    s.a.one_m_beta1 = (float)(1.0 - b1), s.a.one_m_beta2 = (float)(1.0 - b2);
+    s.a.sqrt_bc2 = (float)sqrt(bc2);
+    s.a.eps = 1e-15f;
+    const double lr[6] = {(double)e->cfg.lr_means * e->cfg.scene_scale, e->cfg.lr_scales, e->cfg.lr_quats, e->cfg.lr_dc, e->cfg.lr_rest, e->cfg.lr_opac};
+    for (int i = 0; i < 6; i++)
+        s.step_size[i] = (float)(lr[i] / bc1);
+    return s;
+}
+
 // RawGaussianModel::forward -> gesForward (src/raw_gs_model.cpp:188-367) without autograd: rgb [H,W,3], depth [H,W], alpha [H,W]
 extern "C" int gsb_gs_render(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
                              const float *base_color_dev, float *rgb_dev, float *depth_dev, float *alpha_dev)
@@ -366,18 +382,8 @@ extern "C" int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float 
     raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
     if (e->nUpper > 0)
         raster_bwd(e->recs, e->bins, e->W, e->H, io, nullptr, e->grads, e->stream);
-    // torch::optim::Adam: step count is per optimiser, identical for the 6 of them
     e->adamStep++;
-    const double b1 = (double)0.9f, b2 = (double)0.999f; // float betas widened to double (src/raw_gs_model.cpp:662-663)
-    const double bc1 = 1.0 - pow(b1, e->adamStep), bc2 = 1.0 - pow(b2, e->adamStep);
-    AdamStep s;
-    s.a.beta1 = (float)b1, s.a.beta2 = (float)b2;
-    s.a.one_m_beta1 = (float)(1.0 - b1), s.a.one_m_beta2 = (float)(1.0 - b2);
-    s.a.sqrt_bc2 = (float)sqrt(bc2);
-    s.a.eps = 1e-15f;
-    const double lr[6] = {(double)e->cfg.lr_means * e->cfg.scene_scale, e->cfg.lr_scales, e->cfg.lr_quats, e->cfg.lr_dc, e->cfg.lr_rest, e->cfg.lr_opac};
-    for (int i = 0; i < 6; i++)
-        s.step_size[i] = (float)(lr[i] / bc1);
+    AdamStep s = make_adam_step(e);
     bwd_params_adam(e->p, e->m, e->v, e->touched, s, e->nDev, e->nUpper, cam, e->recs, e->grads, e->aux, e->haveDbg ? &e->dbg : nullptr,
                     e->bins.counters, e->stream);
     GS_CUDA_OK(cudaGetLastError());
@@ -484,7 +490,10 @@ extern "C" int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const flo
         return gs_set_error(__FILE__, __LINE__, "null argument");
     if (!(sc->max_init_scale > 0.f))
         return gs_set_error(__FILE__, __LINE__, "gsb_gs_spawn needs max_init_scale > 0 (bounded-radius KNN)");
-    if (e->nUpper > 0)
+    const float *rRgb = e->spRgb, *rAlpha = e->spAlpha;
+    if (sc->render_rgb_dev && sc->render_alpha_dev)
+        rRgb = (const float *)sc->render_rgb_dev, rAlpha = (const float *)sc->render_alpha_dev; // the caller rendered (multi-GPU)
+    else if (e->nUpper > 0)
         if (gsb_gs_render(e, c2w, fx, fy, cx, cy, depth_map_dev, color_map_dev, e->spRgb, e->spDepth, e->spAlpha))
             return 1;
     SpawnParams sp;
@@ -497,7 +506,9 @@ extern "C" int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const flo
     sp.seed = sc->seed;
     sp.maxScale = sc->max_init_scale, sp.minScale = sc->min_init_scale;
     sp.defaultOpacity = sc->default_opacity;
-    spawn(sp, e->sb, (const float4 *)free_vertex_dev, depth_map_dev, color_map_dev, gt_rgb_dev, e->spRgb, e->spAlpha, e->p, e->nDev, e->cap,
+    sp.rank = sc->rank, sp.world = sc->world;
+    sp.forceRender = (sc->render_rgb_dev && sc->render_alpha_dev) ? 1 : 0;
+    spawn(sp, e->sb, (const float4 *)free_vertex_dev, depth_map_dev, color_map_dev, gt_rgb_dev, rRgb, rAlpha, e->p, e->nDev, e->cap,
           e->touched, e->bins.counters, e->stream);
     // host-side bound until the next gsb_gs_count
     long long up = (long long)e->nUpper + sp.P;
@@ -542,6 +553,56 @@ extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
     }
     default: return gs_set_error(__FILE__, __LINE__, "bad stage id");
     }
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- multi-GPU: the Gaussian set is sharded across ranks.  The GES blend is an order-independent sum, so each
+// rank rasterises its own Gaussians over the whole image into partial sums acc5 = render_colors [H*W*4] + alphas [H*W]; the
+// caller all-reduces acc5 (NCCL) and every rank finishes redundantly on the summed image.  Backward and Adam are rank-local.
+extern "C" int gsb_gs_forward_partial(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
+                                      float *acc5_dev, int for_backward)
+{
+    if (!e || !c2w || !ref_depth_dev || !acc5_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    CamParams cam;
+    make_camera(e, c2w, fx, fy, cx, cy, cam);
+    project_sh_fwd(e->p, e->nDev, e->nUpper, cam, e->recs, e->grads, e->bins, e->tileW, e->tileH, for_backward != 0, e->stream);
+    bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
+    RasterIO io = make_io(e, ref_depth_dev, nullptr, nullptr);
+    io.render4 = acc5_dev, io.alphas = acc5_dev + (size_t)4 * e->W * e->H;
+    e->lastCam = cam;
+    raster_fwd(RASTER_RAW, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_render_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *base_color_dev, const float *acc5_dev, float *rgb_dev,
+                                    float *depth_dev, float *alpha_dev)
+{
+    if (!e || !ref_depth_dev || !base_color_dev || !acc5_dev || !rgb_dev || !depth_dev || !alpha_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    RasterIO io = make_io(e, ref_depth_dev, base_color_dev, nullptr);
+    io.rgb = rgb_dev, io.depth = depth_dev, io.alphas = alpha_dev;
+    composite(RASTER_RENDER, acc5_dev, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_train_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *base_color_dev, const float *gt_rgb_dev,
+                                   const float *acc5_dev)
+{
+    if (!e || !ref_depth_dev || !base_color_dev || !gt_rgb_dev || !acc5_dev)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    RasterIO io = make_io(e, ref_depth_dev, base_color_dev, gt_rgb_dev);
+    e->lastIo = io, e->haveLast = true;
+    composite(RASTER_TRAIN, acc5_dev, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    if (e->nUpper > 0)
+        raster_bwd(e->recs, e->bins, e->W, e->H, io, nullptr, e->grads, e->stream);
+    e->adamStep++;
+    AdamStep s = make_adam_step(e);
+    bwd_params_adam(e->p, e->m, e->v, e->touched, s, e->nDev, e->nUpper, e->lastCam, e->recs, e->grads, e->aux, e->haveDbg ? &e->dbg : nullptr,
+                    e->bins.counters, e->stream);
     GS_CUDA_OK(cudaGetLastError());
     return 0;
 }

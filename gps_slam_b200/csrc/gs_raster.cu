@@ -266,6 +266,76 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
     }
 }
 
+// epilogue of the forward pass on an already accumulated image (multi-GPU: the per-rank partial sums were all-reduced):
+// acc5 = render_colors [P,4] followed by alphas [P].  Same arithmetic as the tail of k_raster_fwd.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_composite(const float *__restrict__ acc5, int W, int H, int tileW, RasterIO io, float invCount)
+{
+    __shared__ float warpLoss[8];
+    const int tile = blockIdx.x;
+    const int tyi = tile / tileW, txi = tile - tyi * tileW;
+    const int tid = threadIdx.x;
+    const int i = tyi * TILE + (tid >> 4), j = txi * TILE + (tid & 15);
+    const bool inside = (i < H) && (j < W);
+    const int pix = i * W + j;
+    const int P = W * H;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, w = 0.f, rdRaw = 0.f;
+    if (inside)
+    {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(acc5) + pix);
+        a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w;
+        w = __ldg(acc5 + (size_t)4 * P + pix);
+        rdRaw = __ldg(&io.refDepth[pix]);
+    }
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    float w1 = w + 1.0f;
+    if (inside)
+    {
+        const float *bc = io.baseColor + (size_t)pix * 3;
+        r0 = (a0 + __ldg(bc + 0) * 1.0f) / w1;
+        r1 = (a1 + __ldg(bc + 1) * 1.0f) / w1;
+        r2 = (a2 + __ldg(bc + 2) * 1.0f) / w1;
+    }
+    if (MODE == RASTER_RENDER)
+    {
+        if (inside)
+        {
+            float bw = rdRaw > 0.f ? 1.0f : 0.0f;
+            float *o = io.rgb + (size_t)pix * 3;
+            o[0] = r0, o[1] = r1, o[2] = r2;
+            io.depth[pix] = (a3 + rdRaw * bw) / (w + bw);
+            io.alphas[pix] = w;
+        }
+        return;
+    }
+    float lsum = 0.f;
+    if (inside)
+    {
+        const float *gt = io.gt + (size_t)pix * 3;
+        float d0 = r0 - __ldg(gt + 0), d1 = r1 - __ldg(gt + 1), d2 = r2 - __ldg(gt + 2);
+        lsum = fabsf(d0) + fabsf(d1) + fabsf(d2);
+        float v0 = d0 > 0.f ? invCount : (d0 < 0.f ? -invCount : 0.f);
+        float v1 = d1 > 0.f ? invCount : (d1 < 0.f ? -invCount : 0.f);
+        float v2 = d2 > 0.f ? invCount : (d2 < 0.f ? -invCount : 0.f);
+        float va = -(v0 * r0 + v1 * r1 + v2 * r2) / w1;
+        io.v_out[pix] = make_float4(v0 / w1, v1 / w1, v2 / w1, va);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
+    if ((tid & 31) == 0)
+        warpLoss[tid >> 5] = lsum;
+    __syncthreads();
+    if (tid == 0)
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            s += warpLoss[k];
+        io.lossTile[tile] = s;
+    }
+}
+
 __global__ void k_pack_v_out(int P, const float *__restrict__ v_render4, const float *__restrict__ v_alphas, float4 *v_out, float *v_depth)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,6 +366,17 @@ void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const Rast
     cudaMemsetAsync(bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), st);
     k_raster_bwd<<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, H, io.refDepth, io.clampRef, io.deltaDepth, io.v_out,
                                           v_depth, grads);
+}
+
+void composite(int mode, const float *acc5, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st)
+{
+    const int T = tileW * tileH;
+    const float invCount = 1.0f / (float)((size_t)3 * W * H);
+    GS_COUNT_LAUNCHES(1);
+    if (mode == RASTER_RENDER)
+        k_composite<RASTER_RENDER><<<T, 256, 0, st>>>(acc5, W, H, tileW, io, invCount);
+    else
+        k_composite<RASTER_TRAIN><<<T, 256, 0, st>>>(acc5, W, H, tileW, io, invCount);
 }
 
 void pack_v_out(int P, const float *v_render4, const float *v_alphas, float4 *v_out, float *v_depth, cudaStream_t st)

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_spawn_select(SpawnParams sp, const floa
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sp.P)
         return;
-    const bool haveGs = *nDev > 0;
+    const bool haveGs = sp.forceRender || *nDev > 0; // with no Gaussian the render equals the TSDF colour and alpha is 0
     float d = depthMap[i];
     float3 v = world_vertex(vertex4, i, sp.voxelSize);
     bool valid = (d > sp.depthMin) && (d < sp.depthMax) && !(v.x + v.y + v.z == 0.f);
@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(256) k_spawn_select(SpawnParams sp, const floa
     bool m = valid && (err > sp.colorErrorThres);
     if (haveGs)
         m = m && (renderAlpha[i] < sp.alphaMax);
+    // multi-GPU: the Gaussian set is sharded by spatial block (4 cm cells, the TSDF block size); each rank spawns its own
+    if (m && sp.world > 1)
+    {
+        int bx = (int)floorf(v.x * 25.0f), by = (int)floorf(v.y * 25.0f), bz = (int)floorf(v.z * 25.0f);
+        unsigned hsh = ((unsigned)bx * 73856093u) ^ ((unsigned)by * 19349669u) ^ ((unsigned)bz * 83492791u);
+        m = (int)(hash_u32(hsh) % (unsigned)sp.world) == sp.rank;
+    }
     // addGaussians keeps a uniformly random subset of the masked pixels (randperm prefix of length ratio * M); here every masked
     // pixel is kept independently with probability ratio (counter-based hash of pixel and seed): same inclusion probability,
     // deterministic, no sort.

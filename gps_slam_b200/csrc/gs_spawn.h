@@ -15,6 +15,8 @@ struct SpawnParams
     unsigned seed;
     float maxScale, minScale; // MODEL.max_init_scale / min_init_scale
     float defaultOpacity;    // MODEL.default_opacities
+    int forceRender;         // 1: renderRgb / renderAlpha are always valid (caller-supplied render)
+    int rank, world;         // multi-GPU: spawn only the Gaussians whose 4 cm block hashes to this rank (world <= 1: all)
 };
 
 struct SpawnBuffers

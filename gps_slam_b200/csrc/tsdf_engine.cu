@@ -219,7 +219,7 @@ static int process_resident(gsb_tsdf *e, const float *gt_c2w)
                 e->trackingFrames++;
             else
                 e->trackingFrames = 0;
-            icp::convert_depth(e->depth_mm, e->depth_f, e->cfg.width, e->cfg.height, st);
+            icp::convert_depth(e->frame.depth_mm, e->depth_f, e->cfg.width, e->cfg.height, st);
             Mat4 scenePose = e->pose_pointCloud.M;
             int rc = icp::track_camera(e->tracker, e->depth_f, e->pointsMap, e->normalsMap, e->cam.fx, e->cam.fy, e->cam.cx, e->cam.cy, scenePose,
                                        e->trackingFrames, &e->pose_d, st);

@@ -42,7 +42,7 @@ class GsConfig(C.Structure):
 class SpawnConfig(C.Structure):
     _fields_ = [("color_error_thres", C.c_float), ("depth_vis_min", C.c_float), ("depth_vis_max", C.c_float), ("alpha_vis_max", C.c_float),
                 ("sample_ratio", C.c_float), ("max_init_scale", C.c_float), ("min_init_scale", C.c_float), ("default_opacity", C.c_float),
-                ("seed", C.c_uint)]
+                ("seed", C.c_uint), ("rank", C.c_int), ("world", C.c_int), ("render_rgb_dev", C.c_void_p), ("render_alpha_dev", C.c_void_p)]
 
 
 (GS_SPLAT_RECORDS, GS_SPLAT_GRADS, GS_TILE_OFFSETS, GS_FLATTEN_IDS, GS_V_OUT, GS_COUNTERS, GS_GRAD_MEANS, GS_GRAD_SCALES, GS_GRAD_QUATS,
@@ -89,6 +89,7 @@ def load_library():
     L.gsb_tsdf_voxel_size.argtypes = [C.c_void_p]
     L.gsb_tsdf_voxel_size.restype = C.c_float
     L.gsb_tsdf_frames_processed.argtypes = [C.c_void_p]
+    L.gsb_tsdf_frames_processed.restype = C.c_int
     L.gsb_tsdf_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.gsb_tsdf_counter.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.gsb_tsdf_run_stage.argtypes = [C.c_void_p, C.c_int]
@@ -119,6 +120,9 @@ def load_library():
     L.gsb_gs_enable_grad_dump.argtypes = [vp, C.c_int]
     L.gsb_gs_run_stage.argtypes = [vp, C.c_int]
     L.gsb_gs_spawn.argtypes = [vp, C.POINTER(SpawnConfig), vp, fl, fl, fl, fl, vp, fl, vp, vp, vp]
+    L.gsb_gs_forward_partial.argtypes = [vp, vp, fl, fl, fl, fl, vp, vp, C.c_int]
+    L.gsb_gs_render_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.gsb_gs_train_finish.argtypes = [vp, vp, vp, vp, vp]
     L.gsb_gs_raycast_maps.argtypes = [vp, vp, vp, vp, fl, vp, vp, vp]
     L.gsb_gs_frame_to_float.argtypes = [vp, vp, vp, vp, vp]
     L.gsb_tsdf_current_rgba_dev.argtypes = [vp]
@@ -205,6 +209,9 @@ class TsdfEngine:
 
     def getVoxelSize(self):
         return self.L.gsb_tsdf_voxel_size(self.h_)
+
+    def frames_processed(self):
+        return self.L.gsb_tsdf_frames_processed(self.h_)
 
     def pose(self):
         M = np.zeros(16, np.float32)
@@ -393,6 +400,19 @@ class GaussianEngine:
         _check(self.L.gsb_gs_train_step(self.h_, _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(ref_depth_dev),
                                         _ptr(base_color_dev), _ptr(gt_rgb_dev)))
 
+    # ---- multi-GPU (Gaussians sharded across ranks): partial forward -> all-reduce by the caller -> finish
+    def forward_partial(self, c2w, intr, ref_depth_dev, acc5, for_backward):
+        c = self._cam(c2w)
+        _check(self.L.gsb_gs_forward_partial(self.h_, _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(ref_depth_dev), _ptr(acc5),
+                                             int(for_backward)))
+
+    def render_finish(self, ref_depth_dev, base_color_dev, acc5, rgb_out, depth_out, alpha_out):
+        _check(self.L.gsb_gs_render_finish(self.h_, _ptr(ref_depth_dev), _ptr(base_color_dev), _ptr(acc5), _ptr(rgb_out), _ptr(depth_out),
+                                           _ptr(alpha_out)))
+
+    def train_finish(self, ref_depth_dev, base_color_dev, gt_rgb_dev, acc5):
+        _check(self.L.gsb_gs_train_finish(self.h_, _ptr(ref_depth_dev), _ptr(base_color_dev), _ptr(gt_rgb_dev), _ptr(acc5)))
+
     def loss(self):
         v = C.c_double(0)
         _check(self.L.gsb_gs_loss(self.h_, C.byref(v)))
@@ -412,10 +432,12 @@ class GaussianEngine:
 
     def addGaussians(self, c2w, intr, free_vertex_ptr, voxel_size, depth_map, color_map, gt_rgb, seed, color_error_thres=0.05,
                      depth_vis_min=0.0, depth_vis_max=5.0, alpha_vis_max=5.0, sample_ratio=0.25, max_init_scale=0.01, min_init_scale=-1.0,
-                     default_opacity=0.5):
-        """initNewGaussians + addGaussians (defaults: configs/release/replica/office0.yaml)"""
+                     default_opacity=0.5, rank=0, world=1, render_rgb=None, render_alpha=None):
+        """initNewGaussians + addGaussians (defaults: configs/release/replica/office0.yaml).  Multi-GPU: pass the all-reduced render
+        of the camera and (rank, world); each rank then spawns only the Gaussians of its own spatial blocks."""
         sc = SpawnConfig(color_error_thres, depth_vis_min, depth_vis_max, alpha_vis_max, sample_ratio, max_init_scale, min_init_scale,
-                         default_opacity, seed & 0xffffffff)
+                         default_opacity, seed & 0xffffffff, rank, world,
+                         None if render_rgb is None else render_rgb.data_ptr(), None if render_alpha is None else render_alpha.data_ptr())
         c = self._cam(c2w)
         _check(self.L.gsb_gs_spawn(self.h_, C.byref(sc), _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(free_vertex_ptr),
                                    voxel_size, _ptr(depth_map), _ptr(color_map), _ptr(gt_rgb)))

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import engine as E
+from . import parallel
 from . import synthetic as syn
 
 DEFAULT_MODE = "train"
@@ -69,14 +70,20 @@ class BufferPool:
 
 
 class SlamPipeline:
-    def __init__(self, intr, mode="train", device=0, stream=None, rank=0, world=1, cfg=None, seed=42, gs_capacity=1 << 21):
+    def __init__(self, intr, mode="train", device=0, stream=None, rank=0, world=1, cfg=None, seed=42, gs_capacity=1 << 21, use_gt_pose=True,
+                 tracker=1):
+        """use_gt_pose=False: online tracking (TSDF.use_gt_pose: false) with the extended (1) or icp (2) tracker.
+        world > 1: Gaussians sharded across ranks (parallel.py); torch.distributed must be initialised by the caller."""
         self.intr, self.mode, self.rank, self.world = intr, mode, rank, world
         self.cfg = dict(OFFICE0, **(cfg or {}))
         c = self.cfg
         self.device = torch.device("cuda", device)
+        self.use_gt_pose = use_gt_pose
         self.tsdf = E.TsdfEngine(intr, voxel_size=c["voxel_size"], mu=c["trunc_dist"], view_frustum_min=c["viewFrustum_min"],
-                                 view_frustum_max=c["viewFrustum_max"], tracker=0, device=device)
+                                 view_frustum_max=c["viewFrustum_max"], tracker=0 if use_gt_pose else tracker, device=device)
         self.W, self.H = intr["width"], intr["height"]
+        self.acc5 = torch.empty(self.W * self.H * 5, dtype=torch.float32, device=self.device) if (world > 1 and mode == "train") else None
+        self.sp_rgb = self.sp_depth = self.sp_alpha = None
         self.gs = E.GaussianEngine(self.W, self.H, capacity=gs_capacity, device=device) if mode == "train" else None
         self.stream = stream
         if stream is not None:
@@ -121,10 +128,13 @@ class SlamPipeline:
     def process_frame(self, idx, rgba_all, depth_all, poses, resident):
         """one iteration of the SLAMTrainCams loop body (slam_pipeline.cpp:69-143)"""
         c2w = np.asarray(poses[idx], np.float32)
+        if not self.use_gt_pose and self.tsdf.frames_processed() == 0:
+            self.tsdf.set_pose(syn.c2w_to_colmajor(c2w))   # the reference re-bases the trajectory on frame 0; here frame 0 is given
+        gt = syn.c2w_to_colmajor(c2w) if self.use_gt_pose else None
         if resident:
-            self.tsdf.ProcessFrameDevice(rgba_all[idx], depth_all[idx], syn.c2w_to_colmajor(c2w))
+            self.tsdf.ProcessFrameDevice(rgba_all[idx], depth_all[idx], gt)
         else:
-            self.tsdf.ProcessFrame(rgba_all[idx], depth_all[idx], syn.c2w_to_colmajor(c2w))
+            self.tsdf.ProcessFrame(rgba_all[idx], depth_all[idx], gt)
         if self.mode == "recon":
             return
         est = self.tsdf.pose()[1].reshape(4, 4).T.copy()      # est_pose = pose_d->GetInvM() as a row-major tensor (:81-82)
@@ -205,11 +215,18 @@ class SlamPipeline:
         cam = self.window[-1]
         c = self.cfg
         before = self.n_gauss
+        extra = {}
+        if self.world > 1:
+            # the sample mask needs the render of ALL Gaussians: partial forward -> all-reduce -> composite
+            if self.sp_rgb is None:
+                self.sp_rgb, self.sp_depth, self.sp_alpha = self.pool.get((self.H, self.W, 3)), self.pool.get((self.H, self.W)), self.pool.get((self.H, self.W))
+            self._forward_all(cam, self.sp_rgb, self.sp_depth, self.sp_alpha)
+            extra = dict(rank=self.rank, world=self.world, render_rgb=self.sp_rgb, render_alpha=self.sp_alpha)
         self.gs.addGaussians(cam.c2w_slam, self.intr, self.tsdf.GetFreeVertex(), self.tsdf.getVoxelSize(), cam.depth_map, cam.color_map,
                              cam.image, seed=self.seed * 7919 + cam.id, color_error_thres=c["color_error_thres"],
                              depth_vis_min=c["depth_vis_min"], depth_vis_max=c["depth_vis_max"], alpha_vis_max=c["alpha_vis_max"],
                              sample_ratio=c["new_gs_sample_ratio"], max_init_scale=c["max_init_scale"], min_init_scale=c["min_init_scale"],
-                             default_opacity=c["default_opacities"])
+                             default_opacity=c["default_opacities"], **extra)
         self.n_gauss = self.gs.getGaussianNum()    # the one host round trip of the cycle (sizes the next 20 iterations' launches)
         self.spawned_last = self.n_gauss - before
 
@@ -226,7 +243,21 @@ class SlamPipeline:
             current[i] = current[-1]
             current.pop()
             cam = cams[ci]
-            self.gs.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image)
+            if self.world > 1:
+                self.gs.forward_partial(cam.c2w_slam, self.intr, cam.depth_map, self.acc5, True)
+                parallel.allreduce_sum_(self.acc5)      # the one collective of an iteration: [H,W,5] fp32 partial image
+                self.gs.train_finish(cam.depth_map, cam.color_map, cam.image, self.acc5)
+            else:
+                self.gs.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image)
+
+    def _forward_all(self, cam, rgb, depth, alpha):
+        """gesForward over the Gaussians of every rank"""
+        if self.world > 1:
+            self.gs.forward_partial(cam.c2w_slam, self.intr, cam.depth_map, self.acc5, False)
+            parallel.allreduce_sum_(self.acc5)
+            self.gs.render_finish(cam.depth_map, cam.color_map, self.acc5, rgb, depth, alpha)
+        else:
+            self.gs.forward(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, rgb, depth, alpha)
 
     def _remove_redundant(self):
         c = self.cfg
@@ -245,7 +276,7 @@ class SlamPipeline:
         """renderEvalImgs body for one camera (slam_pipeline.cpp:588-660): free-view raycast + gesForward"""
         cam = Cam(-1, np.asarray(c2w, np.float32), np.asarray(c2w, np.float32), None)
         self._raycast_by_cam(cam)
-        self.gs.forward(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, rgb, depth, alpha)
+        self._forward_all(cam, rgb, depth, alpha)
         base = cam.color_map.clone()
         self._release(cam)
         return base
@@ -254,7 +285,13 @@ class SlamPipeline:
         s = {"visible_blocks_last_frame": self.tsdf.counter(2), "allocated_blocks": self.tsdf.num_blocks - 1 - self.tsdf.counter(0)}
         if self.gs:
             cnt = self.gs.counters()
-            s.update(gaussians=self.gs.getGaussianNum(), keyframes=len(self.keyframes), opt_cameras=len(self.opt_cams),
+            n = self.gs.getGaussianNum()
+            if self.world > 1:
+                t = torch.tensor([n], device=self.device, dtype=torch.int64)
+                parallel.allreduce_sum_(t)
+                s["gaussians_this_rank"] = n
+                n = int(t.item())
+            s.update(gaussians=n, keyframes=len(self.keyframes), opt_cameras=len(self.opt_cams),
                      last_isects=int(cnt[0]), last_visible=int(cnt[4]), overflow_flags=int(cnt[2]), cycles=self.cycles)
         return s
 
@@ -262,7 +299,8 @@ class SlamPipeline:
         return frames_per_step * self.W * self.H * 6, 64 + (8 if self.gs else 0)
 
     def scaling(self):
-        return "weak"
+        # the frame sequence is fixed; with N GPUs the same Gaussians and the same frames are split N ways
+        return "weak" if self.world == 1 else "strong"
 
     def _time(self, stream, fn, reps, flush):
         ms = []

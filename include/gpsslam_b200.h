@@ -188,6 +188,9 @@ typedef struct gsb_spawn_config
     float sample_ratio;           /* PIPE.new_gs_sample_ratio (0.25)                      */
     float max_init_scale, min_init_scale, default_opacity;   /* MODEL (0.01, -1, 0.5)     */
     unsigned seed;                /* sampling seed (the reference draws torch::randperm)  */
+    int rank, world;              /* multi-GPU: spawn only Gaussians whose 4 cm block hashes to `rank` (world <= 1: all)      */
+    const void *render_rgb_dev;   /* optional: current render [H,W,3] / weight sum [H,W] supplied by the caller (multi-GPU,   */
+    const void *render_alpha_dev; /* after the all-reduce); NULL -> the engine renders the camera itself                      */
 } gsb_spawn_config_t;
 int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const float *c2w, float fx, float fy, float cx, float cy,
                  const void *free_vertex_dev, float voxel_size, const float *depth_map_dev, const float *color_map_dev,
@@ -197,6 +200,16 @@ int gsb_gs_raycast_maps(gsb_gs_t *e, const void *free_vertex_dev, const void *fr
                         float *depth_map_dev, float *color_map_dev, float *conf_map_dev);
 /* Camera::image / Camera::depth (float) from the raw RGBA8 / int16-mm frame */
 int gsb_gs_frame_to_float(gsb_gs_t *e, const void *rgba_dev, const void *depth_mm_dev, float *rgb_dev, float *depth_dev);
+
+/* Multi-GPU: the Gaussian set is sharded across ranks (one engine per GPU).  The GES blend is an order-independent sum, so every
+ * rank rasterises its own Gaussians into partial sums acc5 = render_colors [H*W*4] followed by alphas [H*W]; the caller
+ * all-reduces acc5 (ncclAllReduce sum over NVLink) and every rank finishes on the summed image; backward and Adam are local. */
+int gsb_gs_forward_partial(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
+                           float *acc5_dev, int for_backward);
+int gsb_gs_render_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *base_color_dev, const float *acc5_dev, float *rgb_dev,
+                         float *depth_dev, float *alpha_dev);
+int gsb_gs_train_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *base_color_dev, const float *gt_rgb_dev,
+                        const float *acc5_dev);
 
 /* state read-back for parity tests (synchronises) */
 enum
