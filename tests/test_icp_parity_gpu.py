@@ -84,9 +84,15 @@ def test_tracked_sequence(engine_lib, tracker, n_frames):
         c0 = syn.c2w_to_colmajor(poses[0])
         eng.set_pose(c0)
         ref.set_pose_invM(c0)
+        import torch
         for i in range(n_frames):
             rgba, d = frames[i][0].numpy(), frames[i][1].numpy()
-            eng.ProcessFrame(rgba, d, None)
+            if i % 2:
+                eng.ProcessFrame(rgba, d, None)                      # host buffers
+            else:
+                rd, dd = frames[i][0].cuda(), frames[i][1].cuda()    # frame already resident in HBM
+                eng.ProcessFrameDevice(rd, dd, None)
+                eng.sync()
             ref.process_frame(rgba, d, None)
             ours = eng.pose()[1].reshape(4, 4).T
             theirs = ref.pose()[1].reshape(4, 4).T
