@@ -91,7 +91,57 @@ struct RasterIO
     float *lossTile;        // TRAIN: per-tile sum |rgb - gt|
 };
 
+#ifdef __CUDACC__
+// Conservative pixel-space half extents of the region where a splat can pass the alpha test:
+// alpha = opacity * exp(-sigma) >= 1/255  <=>  sigma <= tau = ln(255 * opacity); {sigma <= tau} is an ellipse whose axis-aligned
+// half extents are sqrt(2 tau c / det) and sqrt(2 tau a / det).  Inflated for rounding; returns false when nothing can pass.
+__device__ __forceinline__ bool alpha_extent(float a, float b, float c, float opac, float &ex, float &ey)
+{
+    float tau = logf(255.0f * opac) * 1.0005f + 1e-3f;
+    if (!(tau > 0.f))
+        return false;
+    float det = a * c - b * b;
+    if (!(det > 0.f) || !(a > 0.f) || !(c > 0.f))
+    {
+        ex = ey = 1e30f; // degenerate conic: no bound
+        return true;
+    }
+    ex = sqrtf(2.0f * tau * c / det) * 1.001f + 0.02f;
+    ey = sqrtf(2.0f * tau * a / det) * 1.001f + 0.02f;
+    return true;
+}
+
+// Pixel rectangle the rasteriser backward visits for one splat: the reference's box j in [int(x)-r+1, int(x)+r],
+// i in [int(y)-r+1, int(y)+r] (rasterize_to_pixels_bwd_ges_new_parallel.cu:76-96) clipped to the image and to the alpha extent --
+// exactly the pixels that can pass the reference's validity tests.  Returns the pixel count (0: nothing to do).
+__device__ __forceinline__ int bwd_rect(float mx, float my, int radius, float a, float b, float c, float opac, int W, int H, int &x0, int &y0,
+                                        int &w, int &h)
+{
+    float ex, ey;
+    x0 = y0 = w = h = 0;
+    if (!alpha_extent(a, b, c, opac, ex, ey))
+        return 0;
+    int xl = max((int)mx - radius + 1, 0), xh = min((int)mx + radius, W - 1);
+    int yl = max((int)my - radius + 1, 0), yh = min((int)my + radius, H - 1);
+    // pixel centre j + 0.5 must lie within mx +- ex
+    float fxl = ceilf(mx - ex - 0.5f), fxh = floorf(mx + ex - 0.5f), fyl = ceilf(my - ey - 0.5f), fyh = floorf(my + ey - 0.5f);
+    if (fxl > (float)xl)
+        xl = (int)fminf(fxl, 1e9f);
+    if (fxh < (float)xh)
+        xh = (int)fmaxf(fxh, -1e9f);
+    if (fyl > (float)yl)
+        yl = (int)fminf(fyl, 1e9f);
+    if (fyh < (float)yh)
+        yh = (int)fmaxf(fyh, -1e9f);
+    if (xl > xh || yl > yh)
+        return 0;
+    x0 = xl, y0 = yl, w = xh - xl + 1, h = yh - yl + 1;
+    return w * h;
+}
+#endif
+
 constexpr int TILE = 16;
+constexpr int BWD_PIXELS_PER_ITEM = 2048;
 constexpr int BWD_GROUPS_PER_ITEM = 64;
 constexpr int PARAMS_PER_GAUSSIAN = 59;
 

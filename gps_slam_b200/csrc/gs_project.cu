@@ -118,11 +118,14 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
                 atomicAdd(&tileCount[ty * tileW + tx], 1);
         if (forBackward)
         {
-            int groups = bwd_groups(o.radius);
-            nItems = (groups + BWD_GROUPS_PER_ITEM - 1) / BWD_GROUPS_PER_ITEM;
-            if (nItems > 1)
+            int rx, ry, rw, rh;
+            int npix = bwd_rect(o.m2x, o.m2y, o.radius, o.ca, o.cb, o.cc, opac, cam.W, cam.H, rx, ry, rw, rh);
+            nItems = (npix + BWD_PIXELS_PER_ITEM - 1) / BWD_PIXELS_PER_ITEM;
+            if (nItems != 1)
             {
-                bits |= 256; // several warps accumulate into this splat's gradient with atomics: start from zero
+                // 0 items: nothing will write this splat's gradient; > 1: several warps accumulate with atomics. Start from zero.
+                if (nItems > 1)
+                    bits |= 256;
                 float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                 grads[g].g0 = z, grads[g].g1 = z, grads[g].g2 = z;
             }

@@ -24,12 +24,17 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__ recs, const int *__restrict__ tileOffsets,
                                                      const int *__restrict__ flattenSorted, int W, int H, int tileW, RasterIO io, float invCount)
 {
-    __shared__ float4 s0[RB], s1[RB], s2[RB];
+    __shared__ float4 s0[RB], s1[RB], s2[RB], s3[RB];
     __shared__ float warpLoss[8];
     const int tile = blockIdx.x;
     const int tyi = tile / tileW, txi = tile - tyi * tileW;
     const int tid = threadIdx.x;
-    const int i = tyi * TILE + (tid >> 4), j = txi * TILE + (tid & 15);
+    // each warp owns an 8 x 4 pixel rectangle of the tile, so that a splat whose alpha extent misses the rectangle is skipped
+    // by the whole warp with one shared-memory read and four compares
+    const int wid = tid >> 5, lane = tid & 31;
+    const int wx0 = txi * TILE + (wid & 1) * 8, wy0 = tyi * TILE + (wid >> 1) * 4;
+    const int i = wy0 + (lane >> 3), j = wx0 + (lane & 7);
+    const float rxlo = (float)wx0 + 0.5f, rxhi = (float)wx0 + 7.5f, rylo = (float)wy0 + 0.5f, ryhi = (float)wy0 + 3.5f;
     const bool inside = (i < H) && (j < W);
     const int pix = i * W + j;
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
@@ -47,9 +52,15 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
         if (idx < end)
         {
             const SplatRec *r = recs + __ldg(&flattenSorted[idx]);
-            s0[tid] = __ldg(&r->q0);
-            s1[tid] = __ldg(&r->q1);
+            const float4 q0 = __ldg(&r->q0), q1 = __ldg(&r->q1);
+            s0[tid] = q0;
+            s1[tid] = q1;
             s2[tid] = __ldg(&r->q2);
+            float ex, ey;
+            if (alpha_extent(q1.x, q1.y, q1.z, q0.z, ex, ey))
+                s3[tid] = make_float4(q0.x - ex, q0.x + ex, q0.y - ey, q0.y + ey);
+            else
+                s3[tid] = make_float4(1e30f, -1e30f, 1e30f, -1e30f);
         }
         __syncthreads();
         const int n = min(RB, end - b);
@@ -57,6 +68,9 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
         {
             for (int t = 0; t < n; t++)
             {
+                const float4 bb = s3[t];
+                if (bb.y < rxlo || bb.x > rxhi || bb.w < rylo || bb.z > ryhi)
+                    continue; // warp-uniform
                 const float4 c = s1[t];
                 if (c.w > cut)
                     continue;
@@ -166,16 +180,14 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
         const float4 q0 = __ldg(&recs[g].q0), q1 = __ldg(&recs[g].q1), q2 = __ldg(&recs[g].q2);
         const int radius = __float_as_int(q0.w);
         const float opac = q0.z;
-        const int x_min = (int)q0.x - radius, y_min = (int)q0.y - radius, y_max = (int)q0.y + radius;
-        const int bw = 2 * radius;
-        const float inv_bw = 1.0f / (float)bw;
-        const float rr = (float)radius;
-        const int groups = (int)((4.0f * rr * rr + 32.0f - 1.0f) / 32.0f);
-        const int g0 = item.y * BWD_GROUPS_PER_ITEM;
-        const int g1 = min(g0 + BWD_GROUPS_PER_ITEM, groups);
+        int rx, ry, rw, rh;
+        const int npix = bwd_rect(q0.x, q0.y, radius, q1.x, q1.y, q1.z, opac, W, H, rx, ry, rw, rh);
+        const float inv_rw = 1.0f / (float)rw;
+        const int p0 = item.y * BWD_PIXELS_PER_ITEM;
+        const int p1 = min(p0 + BWD_PIXELS_PER_ITEM, npix);
         float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, vca = 0.f, vcb = 0.f, vcc = 0.f, vx = 0.f, vy = 0.f, vo = 0.f;
         // two groups (64 box pixels) per step: their image reads are issued together, before either is consumed
-        for (int grp = g0; grp < g1; grp += 2)
+        for (int pb = p0; pb < p1; pb += 64)
         {
             float dxs[2], dys[2], viss[2], alphas[2], rds[2], vdps[2];
             float4 vos[2];
@@ -183,11 +195,11 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
 #pragma unroll
             for (int u = 0; u < 2; u++)
             {
-                const int id = (grp + u) * 32 + lane;
-                const int row = (int)(((float)id + 0.5f) * inv_bw); // exact for id < 2^16, bw <= 200
-                const int col = id - row * bw;
-                const int j = x_min + 1 + col, i = y_min + 1 + row;
-                bool ok = (grp + u < g1) && !(i < 0 || j < 0 || i >= H || j >= W || i > y_max);
+                const int id = pb + u * 32 + lane;
+                const int row = (int)(((float)id + 0.5f) * inv_rw); // exact for id < 2^16, rw <= 200
+                const int col = id - row * rw;
+                const int j = rx + col, i = ry + row;
+                bool ok = id < p1;
                 const float px = (float)j + 0.5f, py = (float)i + 0.5f;
                 const float dx = q0.x - px, dy = q0.y - py;
                 const float sigma = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;

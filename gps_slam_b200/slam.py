@@ -91,6 +91,12 @@ class SlamPipeline:
             if self.gs:
                 self.gs.set_stream(stream.cuda_stream)
         self.pool = BufferPool(self.device)
+        if mode == "train":
+            # image buffers are recycled; allocate the working set up front so that no cudaMalloc (a device-wide sync) lands inside
+            # the frame loop: window + keyframes hold an image, a depth map and a colour map each
+            pre = [self.pool.get((self.H, self.W, 3)) for _ in range(40)] + [self.pool.get((self.H, self.W)) for _ in range(24)]
+            for t in pre:
+                self.pool.put(t)
         self.seed = seed
         self.reset()
 
