@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
                                                      const int *__restrict__ flattenSorted, int W, int H, int tileW, RasterIO io, float invCount)
 {
     __shared__ float4 s0[RB], s1[RB], s2[RB], s3[RB];
+    __shared__ unsigned char wlist[8][RB]; // per warp: batch slots whose alpha extent touches the warp's rectangle, ascending
     __shared__ float warpLoss[8];
     const int tile = blockIdx.x;
     const int tyi = tile / tileW, txi = tile - tyi * tileW;
@@ -64,13 +65,30 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
         }
         __syncthreads();
         const int n = min(RB, end - b);
-        if (inside)
+        // the warp tests the batch against its rectangle cooperatively (one splat per lane, 8 rounds) and keeps the survivors
+        // in order; the pixel loop below then only visits splats that can touch one of the warp's 32 pixels
+        int ns = 0;
+#pragma unroll
+        for (int k = 0; k < RB / 32; k++)
         {
-            for (int t = 0; t < n; t++)
+            const int t = k * 32 + lane;
+            bool pass = false;
+            if (t < n)
             {
                 const float4 bb = s3[t];
-                if (bb.y < rxlo || bb.x > rxhi || bb.w < rylo || bb.z > ryhi)
-                    continue; // warp-uniform
+                pass = !(bb.y < rxlo || bb.x > rxhi || bb.w < rylo || bb.z > ryhi);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (pass)
+                wlist[wid][ns + __popc(m & ((1u << lane) - 1u))] = (unsigned char)t;
+            ns += __popc(m);
+        }
+        __syncwarp();
+        if (inside)
+        {
+            for (int q = 0; q < ns; q++)
+            {
+                const int t = wlist[wid][q];
                 const float4 c = s1[t];
                 if (c.w > cut)
                     continue;
@@ -185,7 +203,9 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
         const float inv_rw = 1.0f / (float)rw;
         const int p0 = item.y * BWD_PIXELS_PER_ITEM;
         const int p1 = min(p0 + BWD_PIXELS_PER_ITEM, npix);
-        float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, vca = 0.f, vcb = 0.f, vcc = 0.f, vx = 0.f, vy = 0.f, vo = 0.f;
+        // gradient sums; the conic / mean gradients are accumulated as moments of t = v_sigma over (dx, dy):
+        // v_conic = (Sxx/2, Sxy, Syy/2), v_mean2d = (a Sx + b Sy, b Sx + c Sy)
+        float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f, vo = 0.f;
         // two groups (64 box pixels) per step: their image reads are issued together, before either is consumed
         for (int pb = p0; pb < p1; pb += 64)
         {
@@ -234,16 +254,20 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
                 const float v_alpha = q2.x * vo4.x + q2.y * vo4.y + q2.z * vo4.z + q1.w * vdp + vo4.w;
                 if (opac * vis <= 0.999f)
                 {
-                    const float v_sigma = -opac * vis * v_alpha;
-                    vca += 0.5f * v_sigma * dx * dx;
-                    vcb += v_sigma * dx * dy;
-                    vcc += 0.5f * v_sigma * dy * dy;
-                    vx += v_sigma * (q1.x * dx + q1.y * dy);
-                    vy += v_sigma * (q1.y * dx + q1.z * dy);
-                    vo += vis * v_alpha;
+                    const float qv = vis * v_alpha;
+                    const float t = -opac * qv;
+                    const float tx = t * dx, ty = t * dy;
+                    sxx += tx * dx;
+                    sxy += tx * dy;
+                    syy += ty * dy;
+                    sx += tx;
+                    sy += ty;
+                    vo += qv;
                 }
             }
         }
+        float vca = 0.5f * sxx, vcb = sxy, vcc = 0.5f * syy;
+        float vx = q1.x * sx + q1.y * sy, vy = q1.y * sx + q1.z * sy;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1)
         {
