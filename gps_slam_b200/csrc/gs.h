@@ -64,7 +64,7 @@ struct Bins
     int *flatten;       // [isectCap] scatter order (arbitrary within a tile)
     int *flattenSorted; // [isectCap] ascending Gaussian id within each tile  == reference flatten_ids
     int isectCap;
-    int2 *items;        // [itemCap] (gaussian id, chunk of BWD_GROUPS_PER_ITEM pixel groups)
+    int4 *items;        // [itemCap] (gaussian id, first rect-linear pixel, x0 | y0 << 16, w | h << 16) of <= BWD_PIXELS_PER_ITEM pixels
     int itemCap;
     int *counters;      // [CNT_TOTAL]
 };

@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_coeffs(const ParamPtrs &p, int g, float *cl
 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__restrict__ nDev, CamParams cam, SplatRec *__restrict__ recs,
-                                                     SplatGrad *__restrict__ grads, int *tileCount, int tileW, int tileH, int2 *items,
+                                                     SplatGrad *__restrict__ grads, int *tileCount, int tileW, int tileH, int4 *items,
                                                      int itemCap, int *counters, int forBackward)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
             rest[i] = src[i];
     }
     __syncwarp();
-    int nItems = 0;
+    int nItems = 0, rectXY = 0, rectWH = 0;
     int bits = 0;
     float col[3] = {0.f, 0.f, 0.f};
     float opac = 0.f;
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
             int rx, ry, rw, rh;
             int npix = bwd_rect(o.m2x, o.m2y, o.radius, o.ca, o.cb, o.cc, opac, cam.W, cam.H, rx, ry, rw, rh);
             nItems = (npix + BWD_PIXELS_PER_ITEM - 1) / BWD_PIXELS_PER_ITEM;
+            rectXY = rx | (ry << 16), rectWH = rw | (rh << 16);
             if (nItems != 1)
             {
                 // 0 items: nothing will write this splat's gradient; > 1: several warps accumulate with atomics. Start from zero.
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
         if (base + nItems <= itemCap)
         {
             for (int i = 0; i < nItems; i++)
-                items[base + i] = make_int2(g, i);
+                items[base + i] = make_int4(g, i * BWD_PIXELS_PER_ITEM, rectXY, rectWH);
         }
         else
             atomicOr(&counters[CNT_OVERFLOW], 2);

@@ -170,7 +170,37 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__ recs, const int2 *__restrict__ items, int *counters, int itemCap,
+// Sum 16 per-lane values over the warp with 16 shuffles (instead of 16 x 5): at each halving step a lane keeps one half of its
+// values and hands the other half to its partner.  Returns, in lane l, the warp total of slot l >> 1 (each total is held twice).
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane)
+{
+    const unsigned full = 0xffffffffu;
+    float w8[8], w4[4], w2[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        float send = h8 ? w8[i] : w8[i + 4], keep = h8 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+    {
+        float send = h4 ? w4[i] : w4[i + 2], keep = h4 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    float send = h2 ? w2[0] : w2[1], keep = h2 ? w2[1] : w2[0];
+    float w1 = keep + __shfl_xor_sync(full, send, 2);
+    return w1 + __shfl_xor_sync(full, w1, 1);
+}
+
+__global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__ recs, const int4 *__restrict__ items, int *counters, int itemCap,
                                                      int W, int H, const float *__restrict__ refDepth, int clampRef, float deltaDepth,
                                                      const float4 *__restrict__ v_out, const float *__restrict__ v_depthImg,
                                                      SplatGrad *__restrict__ grads)
@@ -192,16 +222,16 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
                 break;
             itEnd = min(it + GRAB, nItems);
         }
-        const int2 item = __ldg(&items[it]);
+        const int4 item = __ldg(&items[it]);
         it++;
         const int g = item.x;
         const float4 q0 = __ldg(&recs[g].q0), q1 = __ldg(&recs[g].q1), q2 = __ldg(&recs[g].q2);
-        const int radius = __float_as_int(q0.w);
         const float opac = q0.z;
-        int rx, ry, rw, rh;
-        const int npix = bwd_rect(q0.x, q0.y, radius, q1.x, q1.y, q1.z, opac, W, H, rx, ry, rw, rh);
+        // the pixel rectangle was computed once by the projection pass (bwd_rect)
+        const int rx = item.z & 0xffff, ry = item.z >> 16, rw = item.w & 0xffff, rh = item.w >> 16;
+        const int npix = rw * rh;
         const float inv_rw = 1.0f / (float)rw;
-        const int p0 = item.y * BWD_PIXELS_PER_ITEM;
+        const int p0 = item.y;
         const int p1 = min(p0 + BWD_PIXELS_PER_ITEM, npix);
         // gradient sums; the conic / mean gradients are accumulated as moments of t = v_sigma over (dx, dy):
         // v_conic = (Sxx/2, Sxy, Syy/2), v_mean2d = (a Sx + b Sy, b Sx + c Sy)
@@ -266,38 +296,24 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
                 }
             }
         }
-        float vca = 0.5f * sxx, vcb = sxy, vcc = 0.5f * syy;
-        float vx = q1.x * sx + q1.y * sy, vy = q1.y * sx + q1.z * sy;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1)
+        // slots follow the float layout of SplatGrad: (vx, vy, vo, vd | vca, vcb, vcc, - | vr, vg, vb, -)
+        float v16[16];
+        v16[0] = q1.x * sx + q1.y * sy, v16[1] = q1.y * sx + q1.z * sy, v16[2] = vo, v16[3] = vd;
+        v16[4] = 0.5f * sxx, v16[5] = sxy, v16[6] = 0.5f * syy, v16[7] = 0.f;
+        v16[8] = vr, v16[9] = vg, v16[10] = vb, v16[11] = 0.f;
+        v16[12] = v16[13] = v16[14] = v16[15] = 0.f;
+        const float total = warp_reduce16(v16, lane);
+        const int slot = lane >> 1;
+        if ((lane & 1) == 0 && slot < 12)
         {
-            vr += __shfl_xor_sync(0xffffffffu, vr, d);
-            vg += __shfl_xor_sync(0xffffffffu, vg, d);
-            vb += __shfl_xor_sync(0xffffffffu, vb, d);
-            vd += __shfl_xor_sync(0xffffffffu, vd, d);
-            vca += __shfl_xor_sync(0xffffffffu, vca, d);
-            vcb += __shfl_xor_sync(0xffffffffu, vcb, d);
-            vcc += __shfl_xor_sync(0xffffffffu, vcc, d);
-            vx += __shfl_xor_sync(0xffffffffu, vx, d);
-            vy += __shfl_xor_sync(0xffffffffu, vy, d);
-            vo += __shfl_xor_sync(0xffffffffu, vo, d);
-        }
-        if (lane == 0)
-        {
-            SplatGrad *o = grads + g;
+            float *f = reinterpret_cast<float *>(grads + g) + slot;
             if (__float_as_int(q2.w) & 256)
             {
-                float *f = reinterpret_cast<float *>(o);
-                atomicAdd(f + 0, vx), atomicAdd(f + 1, vy), atomicAdd(f + 2, vo), atomicAdd(f + 3, vd);
-                atomicAdd(f + 4, vca), atomicAdd(f + 5, vcb), atomicAdd(f + 6, vcc);
-                atomicAdd(f + 8, vr), atomicAdd(f + 9, vg), atomicAdd(f + 10, vb);
+                if (slot != 7 && slot != 11)
+                    atomicAdd(f, total);
             }
             else
-            {
-                o->g0 = make_float4(vx, vy, vo, vd);
-                o->g1 = make_float4(vca, vcb, vcc, 0.f);
-                o->g2 = make_float4(vr, vg, vb, 0.f);
-            }
+                *f = total;
         }
     }
 }
