@@ -488,6 +488,7 @@ __device__ __forceinline__ bool integrate_voxel(uint2 &raw, int gx, int gy, int 
 
 constexpr int INT_THREADS = 256;
 constexpr int INT_STAGES = 4;
+constexpr int INT_DESC = 128; // descriptor ring (two halves of 64)
 
 __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict__ vba, const HashEntry *__restrict__ table,
                                                                 const int *__restrict__ visIds, const int *__restrict__ nVis,
@@ -496,9 +497,11 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
 {
     __shared__ __align__(128) uint2 buf[INT_STAGES][SDF_BLOCK_SIZE3];
     __shared__ __align__(8) unsigned long long full[INT_STAGES];
-    __shared__ int sPtr[INT_STAGES];
-    __shared__ short4 sPos[INT_STAGES];
     __shared__ int sDirty[INT_STAGES];
+    // block descriptors (VBA pointer + block position) of this CTA's next INT_DESC work items, fetched by all threads at once:
+    // the two dependent global loads (visible id -> hash entry) are then off the single-thread TMA issue path
+    __shared__ int dPtr[INT_DESC];
+    __shared__ short4 dPos[INT_DESC];
 
     const int n = *nVis;
     const int tid = threadIdx.x;
@@ -508,22 +511,33 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
             mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
 
     // work items of this CTA: i = blockIdx.x + k * gridDim.x
     const int myCount = (n > (int)blockIdx.x) ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
+    auto load_desc = [&](int kBase) {
+        // descriptors kBase .. kBase + INT_DESC/2 - 1 go to the half of the ring selected by (kBase / (INT_DESC/2)) & 1
+        int k = kBase + tid;
+        if (tid < INT_DESC / 2 && k < myCount)
+        {
+            int slot = __ldg(&visIds[blockIdx.x + k * gridDim.x]);
+            HashEntry e = load_entry(table, slot);
+            dPtr[k % INT_DESC] = e.ptr;
+            dPos[k % INT_DESC] = make_short4(e.px, e.py, e.pz, 0);
+        }
+    };
+    load_desc(0);
+    load_desc(INT_DESC / 2);
+    __syncthreads();
+
     auto issue = [&](int k) {
         // executed by thread 0 only
         int s = k % INT_STAGES;
-        int slot = visIds[blockIdx.x + k * gridDim.x];
-        HashEntry e = load_entry(table, slot);
-        sPtr[s] = e.ptr;
-        sPos[s] = make_short4(e.px, e.py, e.pz, 0);
-        if (e.ptr >= 0)
+        int ptr = dPtr[k % INT_DESC];
+        if (ptr >= 0)
         {
             mbar_expect_tx(&full[s], SDF_BLOCK_SIZE3 * 8);
-            tma_load_1d(&buf[s][0], vba + (size_t)e.ptr * SDF_BLOCK_SIZE3, SDF_BLOCK_SIZE3 * 8, &full[s]);
+            tma_load_1d(&buf[s][0], vba + (size_t)ptr * SDF_BLOCK_SIZE3, SDF_BLOCK_SIZE3 * 8, &full[s]);
         }
         else
             mbar_expect_tx(&full[s], 0); // nothing to load: complete the phase so stage parity stays in step
@@ -537,6 +551,9 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
     for (int k = 0; k < myCount; k++)
     {
         int s = k % INT_STAGES;
+        // refill the half of the descriptor ring that has just been consumed (items k - INT_DESC/2 .. k - 1)
+        if (k > 0 && (k % (INT_DESC / 2)) == 0)
+            load_desc(k + INT_DESC / 2);
         // prefetch item k + STAGES-1 into the stage freed by item k-1 (its store must have finished READING smem)
         if (tid == 0)
         {
@@ -549,11 +566,11 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
             sDirty[s] = 0;
         }
         __syncthreads();
-        int ptr = sPtr[s];
+        int ptr = dPtr[k % INT_DESC];
         mbar_wait(&full[s], (unsigned)((k / INT_STAGES) & 1));
         if (ptr >= 0)
         {
-            short4 bp = sPos[s];
+            short4 bp = dPos[k % INT_DESC];
             int gx0 = (int)bp.x * SDF_BLOCK_SIZE, gy0 = (int)bp.y * SDF_BLOCK_SIZE, gz0 = (int)bp.z * SDF_BLOCK_SIZE;
             bool any = false;
 #pragma unroll
@@ -1030,7 +1047,7 @@ void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, c
     if (variant == 1)
         k_integrate_direct<<<148 * 4, 512, 0, st>>>(s.vba, s.table, s.visIds, s.state + 2, P, f.depth_f, f.rgba);
     else
-        k_integrate_tma<<<148 * 4, INT_THREADS, 0, st>>>(s.vba, s.table, s.visIds, s.state + 2, P, f.depth_f, f.rgba);
+        k_integrate_tma<<<148 * 5, INT_THREADS, 0, st>>>(s.vba, s.table, s.visIds, s.state + 2, P, f.depth_f, f.rgba);
 }
 
 void expected_depth_live(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st)
