@@ -39,12 +39,14 @@ def intr_of(K, W, H):
     return dict(width=W, height=H, fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]))
 
 
-def compare_iteration(N, W, H, seed, verbose=False, **splat_kw):
+def compare_iteration(N, W, H, seed, verbose=False, checker=None, **splat_kw):
+    """checker: function with gs_oracle.ges_iteration's signature producing the expected values -- the numpy oracle by
+    default, oracle.gsplat_ref.ges_iteration (the reference's own CUDA kernels) in tests/test_gs_reference_gpu.py"""
     from gps_slam_b200.engine import GaussianEngine
     p = random_splats(N, seed=seed, **splat_kw)
     c2w, K = camera(W, H, seed)
     ref_depth, base, gt = scene_images(W, H, seed)
-    it = go.ges_iteration(p, c2w, K, W, H, ref_depth, base, gt)
+    it = (checker or go.ges_iteration)(p, c2w, K, W, H, ref_depth, base, gt)
     intr = intr_of(K, W, H)
     dev = torch.device("cuda", 0)
     rd_d, base_d, gt_d = [torch.from_numpy(a).to(dev).contiguous() for a in (ref_depth, base, gt)]
