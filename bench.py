@@ -96,6 +96,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the newest committed
+    `ncu --set full` capture (profiles/*_avg.json, written by tools/ncu_summary.py); {} when none is committed"""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_*_avg.json")))
+    if not files:
+        return {}, None
+    with open(files[-1]) as f:
+        k = json.load(f)["kernels"]
+    return {name.split("::")[-1].split("<")[0]: v["dram_bytes_per_launch"] for name, v in k.items()}, os.path.basename(files[-1])
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -288,6 +300,11 @@ def main():
         roofline = pipe.time_dominant_kernel(stream, peak, reps=args.timing_reps)
         torch.cuda.nvtx.range_pop()
         roofline["peak_source"] = peak_src
+        traffic, src = ncu_traffic()
+        for r in (roofline, roofline.get("tsdf_integrate") or {}):
+            if r.get("kernel") in traffic:
+                r["traffic"] = traffic[r["kernel"]]
+                r["traffic_source"] = "profiles/" + src
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(intr, poses, rgba, depth)

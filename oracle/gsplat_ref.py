@@ -60,10 +60,11 @@ class RefGaussians:
         import torch
         o = ops()
         dev = self.dev
-        c2w = torch.as_tensor(np.asarray(c2w, np.float32), device=dev)
-        Ks = torch.as_tensor(np.asarray(K, np.float32), device=dev)
-        ref_depth = torch.as_tensor(np.asarray(ref_depth_raw, np.float32), device=dev).reshape(1, H, W, 1)
-        base = torch.as_tensor(np.asarray(base_color, np.float32), device=dev).reshape(1, H, W, 3)
+        def t(x):
+            return x.to(dev, torch.float32) if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, np.float32), device=dev)
+        c2w, Ks = t(c2w), t(K)
+        ref_depth = t(ref_depth_raw).reshape(1, H, W, 1)
+        base = t(base_color).reshape(1, H, W, 3)
         tile_w, tile_h = -(-W // tile_size), -(-H // tile_size)
         cam_T = c2w[:3, 3:4]
         ref_clamped = torch.where(ref_depth < 0.01, torch.full_like(ref_depth, 1000.0), ref_depth)
@@ -71,7 +72,7 @@ class RefGaussians:
         means = self.p["means"].contiguous()
         scales = torch.exp(self.p["scales"]).contiguous()
         radiis, means2d, depths, conics = o.fully_fused_projection(means, self.p["quats"], scales, viewmat.unsqueeze(0), Ks.unsqueeze(0),
-                                                                   W, H, 0.3, 0.01, 1e10, 0.0)
+                                                                   W, H, 0.3, 0.01, 1e10, 0.0)[:4]
         if max_radii > 0:
             radiis = torch.clamp_max(radiis, max_radii)
         shs = torch.cat([self.p["featuresDc"][:, None, :], self.p["featuresRest"]], 1)
@@ -95,7 +96,7 @@ class RefGaussians:
         if keep:
             out.update(viewmat=viewmat, radii=radiis, means2d=means2d, depths=depths, conics=conics, sh_raw=sh_raw, colors=colors,
                        opac=opac, tiles_per_gauss=tpg, isect_ids=isect_ids, flatten_ids=flatten_ids, group_gs_ids=group_gs_ids,
-                       group_starts=group_starts, tile_offsets=offsets, render=render, colors4=colors4)
+                       group_starts=group_starts, tile_offsets=offsets, render=render, colors4=colors4, wsum=wsum)
         return out
 
     def train_iteration(self, c2w, K, W, H, ref_depth_raw, base_color, gt_rgb, step=True, **kw):
@@ -105,7 +106,7 @@ class RefGaussians:
         for k in self.KEYS:
             self.p[k].grad = None
         r = self.forward(c2w, K, W, H, ref_depth_raw, base_color, keep=True, **kw)
-        for k in ("means2d", "conics", "colors4", "opac", "render", "alpha"):
+        for k in ("means2d", "conics", "colors4", "opac", "render", "wsum"):
             r[k].retain_grad()
         gt = torch.as_tensor(np.asarray(gt_rgb, np.float32), device=self.dev)
         loss = torch.abs(gt - r["rgb"]).mean()
@@ -124,8 +125,8 @@ class RefGaussians:
             colors=n(r["colors"])[0], sh_raw=n(r["sh_raw"])[0], tiles_per_gauss=n(r["tiles_per_gauss"]).reshape(-1),
             isect_ids=n(r["isect_ids"]), flatten_ids=n(r["flatten_ids"]), tile_offsets=n(r["tile_offsets"]).reshape(-1),
             group_gs_ids=n(r["group_gs_ids"]), group_starts=n(r["group_starts"]),
-            render=n(r["render"])[0], alphas=n(r["alpha"])[..., 0], rgb=n(r["rgb"]), depth=n(r["depth"])[..., 0], loss=float(loss),
-            v_render=n(r["render"].grad)[0], v_alphas=n(r["alpha"].grad)[..., 0],
+            render=n(r["render"])[0], alphas=n(r["alpha"])[..., 0], rgb=n(r["rgb"]), depth=n(r["depth"])[..., 0], loss=float(loss.detach()),
+            v_render=n(r["render"].grad)[0], v_alphas=n(r["wsum"].grad)[0, ..., 0],
             v_means2d=n(r["means2d"].grad)[0], v_conics=n(r["conics"].grad)[0], v_colors=n(r["colors4"].grad)[0],
             v_opacities=n(r["opac"].grad).reshape(N), grads=grads)
 

