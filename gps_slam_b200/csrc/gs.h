@@ -58,9 +58,10 @@ enum
 
 struct Bins
 {
-    int *tileCount;     // [T+1] zero between iterations
+    int *segCount;      // [T*BIN_CHUNKS] intersections per (tile, id-range chunk); doubles as the scatter cursor; zero between iterations
+    int *segOff;        // [T*BIN_CHUNKS] offset of the segment inside its tile's list
+    int *tileCount;     // [T+1] per-tile totals
     int *tileOffsets;   // [T+1] exclusive scan; [T] = n_isects
-    int *tileCursor;    // [T]
     int *flatten;       // [isectCap] scatter order (arbitrary within a tile)
     int *flattenSorted; // [isectCap] ascending Gaussian id within each tile  == reference flatten_ids
     int isectCap;
@@ -89,6 +90,7 @@ struct RasterIO
     float *depth;           // RENDER
     float4 *v_out;          // TRAIN: (v_render_r, v_render_g, v_render_b, v_render_alpha)
     float *lossTile;        // TRAIN: per-tile sum |rgb - gt|
+    float *cut;             // RAW / TRAIN: per-pixel depth-test threshold (clamped refDepth + deltaDepth), read by the backward
 };
 
 #ifdef __CUDACC__
@@ -141,6 +143,8 @@ __device__ __forceinline__ int bwd_rect(float mx, float my, int radius, float a,
 #endif
 
 constexpr int TILE = 16;
+constexpr int BIN_CHUNKS = 64; // id-range chunks of the counting sort by (tile, chunk)
+inline int bin_chunk_size(int nUpper) { return nUpper > BIN_CHUNKS ? (nUpper + BIN_CHUNKS - 1) / BIN_CHUNKS : 1; }
 constexpr int BWD_PIXELS_PER_ITEM = 2048;
 constexpr int BWD_GROUPS_PER_ITEM = 64;
 constexpr int PARAMS_PER_GAUSSIAN = 59;

@@ -32,6 +32,7 @@ struct gsb_gs
     Bins bins;
     float4 *v_out;
     float *v_depth;
+    float *cutImg;
     float *lossTile;
     double *lossDev;
     int *scanTmp;
@@ -137,13 +138,15 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     e->bins.itemCap = cfg->item_capacity > 0 ? cfg->item_capacity : (1 << 23);
     rc |= dev_alloc(e, &e->bins.tileCount, (size_t)e->T + 1);
     rc |= dev_alloc(e, &e->bins.tileOffsets, (size_t)e->T + 1);
-    rc |= dev_alloc(e, &e->bins.tileCursor, (size_t)e->T + 1);
+    rc |= dev_alloc(e, &e->bins.segCount, (size_t)e->T * BIN_CHUNKS);
+    rc |= dev_alloc(e, &e->bins.segOff, (size_t)e->T * BIN_CHUNKS);
     rc |= dev_alloc(e, &e->bins.flatten, (size_t)e->bins.isectCap);
     rc |= dev_alloc(e, &e->bins.flattenSorted, (size_t)e->bins.isectCap);
     rc |= dev_alloc(e, &e->bins.items, (size_t)e->bins.itemCap);
     rc |= dev_alloc(e, &e->bins.counters, (size_t)CNT_TOTAL);
     rc |= dev_alloc(e, &e->v_out, P);
     rc |= dev_alloc(e, &e->v_depth, P);
+    rc |= dev_alloc(e, &e->cutImg, P);
     rc |= dev_alloc(e, &e->lossTile, (size_t)e->T);
     rc |= dev_alloc(e, &e->lossDev, 1);
     rc |= dev_alloc(e, &e->scanTmp, (size_t)e->cap / 1024 + 2);
@@ -173,6 +176,7 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     }
     cudaMemsetAsync(e->nDev, 0, sizeof(int), e->stream);
     cudaMemsetAsync(e->bins.tileCount, 0, sizeof(int) * (e->T + 1), e->stream);
+    cudaMemsetAsync(e->bins.segCount, 0, sizeof(int) * (size_t)e->T * BIN_CHUNKS, e->stream);
     cudaMemsetAsync(e->bins.counters, 0, sizeof(int) * CNT_TOTAL, e->stream);
     cudaMemsetAsync(e->touched, 0, (size_t)e->cap, e->stream);
     cudaMemsetAsync(e->lossTile, 0, sizeof(float) * e->T, e->stream);
@@ -329,7 +333,7 @@ static RasterIO make_io(const gsb_gs *e, const float *ref_depth, const float *ba
     io.refDepth = ref_depth, io.baseColor = base_color, io.gt = gt;
     io.deltaDepth = e->cfg.delta_depth;
     io.clampRef = 1;
-    io.v_out = e->v_out, io.lossTile = e->lossTile;
+    io.v_out = e->v_out, io.lossTile = e->lossTile, io.cut = e->cutImg;
     return io;
 }
 
@@ -529,12 +533,12 @@ extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
     {
     case 0:
         GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
-        GS_CUDA_OK(cudaMemsetAsync(e->bins.tileCount, 0, sizeof(int) * (e->T + 1), e->stream));
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.segCount, 0, sizeof(int) * (size_t)e->T * BIN_CHUNKS, e->stream));
         project_sh_fwd(e->p, e->nDev, e->nUpper, e->lastCam, e->recs, e->grads, e->bins, e->tileW, e->tileH, true, e->stream);
         break;
     case 1: // binning consumes the tile counts, so it is always timed together with the projection that produces them
         GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
-        GS_CUDA_OK(cudaMemsetAsync(e->bins.tileCount, 0, sizeof(int) * (e->T + 1), e->stream));
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.segCount, 0, sizeof(int) * (size_t)e->T * BIN_CHUNKS, e->stream));
         project_sh_fwd(e->p, e->nDev, e->nUpper, e->lastCam, e->recs, e->grads, e->bins, e->tileW, e->tileH, true, e->stream);
         bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
         break;

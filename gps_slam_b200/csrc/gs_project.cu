@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_coeffs(const ParamPtrs &p, int g, float *cl
 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__restrict__ nDev, CamParams cam, SplatRec *__restrict__ recs,
-                                                     SplatGrad *__restrict__ grads, int *tileCount, int tileW, int tileH, int4 *items,
+                                                     SplatGrad *__restrict__ grads, int *segCount, int chunkSize, int tileW, int tileH, int4 *items,
                                                      int itemCap, int *counters, int forBackward)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
         }
         int x0, y0, x1, y1;
         tile_rect(o.m2x, o.m2y, o.radius, tileW, tileH, x0, y0, x1, y1);
+        const int chunk = g / chunkSize; // id-range chunk: bins are counted per (tile, chunk) so that the scatter is ordered across chunks
         for (int ty = y0; ty < y1; ty++)
             for (int tx = x0; tx < x1; tx++)
-                atomicAdd(&tileCount[ty * tileW + tx], 1);
+                atomicAdd(&segCount[(ty * tileW + tx) * BIN_CHUNKS + chunk], 1);
         if (forBackward)
         {
             int rx, ry, rw, rh;
@@ -180,8 +181,39 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
     recs[g] = r;
 }
 
+// Binning = counting sort by (tile, id-range chunk).  The Gaussians are cut into BIN_CHUNKS consecutive id ranges; the projection
+// pass counts intersections per (tile, chunk) segment, k_seg_scan turns the counts of a tile into segment offsets, k_scan_tiles
+// scans the tile totals, k_scatter_tiles drops each id into its segment (order inside a segment is arbitrary, segments of a tile
+// are in ascending id-range order), and k_sort_tiles orders the few ids of every segment.  Result: ascending Gaussian id within
+// each tile = the order of the reference's stable radix sort by tile id (isect_tiles_no_depth.cu:233-301), with the same-address
+// atomic pressure spread over BIN_CHUNKS x more counters and a sort of ~5-element segments instead of whole tile lists.
+__global__ void __launch_bounds__(256) k_seg_scan(int *segCount, int *segOff, int *tileCount, int T)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (t >= T)
+        return;
+    static_assert(BIN_CHUNKS == 64, "one int2 per lane");
+    int2 *cnt = reinterpret_cast<int2 *>(segCount + (size_t)t * BIN_CHUNKS) + lane;
+    const int2 v = *cnt;
+    const int sum = v.x + v.y;
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += n;
+    }
+    const int excl = incl - sum;
+    reinterpret_cast<int2 *>(segOff + (size_t)t * BIN_CHUNKS)[lane] = make_int2(excl, excl + v.x);
+    *cnt = make_int2(0, 0); // the counters become the scatter cursors
+    if (lane == 31)
+        tileCount[t] = incl;
+}
+
 // exclusive scan of the per-tile counts (T + 1 <= a few 10^4 entries) by one CTA; also re-arms the per-iteration counters
-__global__ void __launch_bounds__(1024) k_scan_tiles(int *tileCount, int *tileOffsets, int *tileCursor, int T, int isectCap, int *counters)
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int *tileCount, int *tileOffsets, int T, int isectCap, int *counters)
 {
     __shared__ int warpSums[32];
     __shared__ int carry;
@@ -220,11 +252,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(int *tileCount, int *tileOf
         __syncthreads();
         int excl = carry + warpSums[wid] + incl - v;
         if (i < T)
-        {
             tileOffsets[i] = min(excl, isectCap);
-            tileCursor[i] = 0;
-            tileCount[i] = 0;
-        }
         __syncthreads();
         if (tid == 1023)
             carry = excl + v;
@@ -246,8 +274,8 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(int *tileCount, int *tileOf
 }
 
 __global__ void __launch_bounds__(256) k_scatter_tiles(const SplatRec *__restrict__ recs, const int *__restrict__ nDev,
-                                                        const int *__restrict__ tileOffsets, int *tileCursor, int *flatten, int isectCap, int tileW,
-                                                        int tileH)
+                                                        const int *__restrict__ tileOffsets, const int *__restrict__ segOff, int *segCursor,
+                                                        int chunkSize, int *flatten, int isectCap, int tileW, int tileH)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= *nDev)
@@ -258,39 +286,90 @@ __global__ void __launch_bounds__(256) k_scatter_tiles(const SplatRec *__restric
         return;
     int x0, y0, x1, y1;
     tile_rect(q0.x, q0.y, radius, tileW, tileH, x0, y0, x1, y1);
+    const int chunk = g / chunkSize;
     for (int ty = y0; ty < y1; ty++)
         for (int tx = x0; tx < x1; tx++)
         {
-            int t = ty * tileW + tx;
-            int pos = tileOffsets[t] + atomicAdd(&tileCursor[t], 1);
+            const int t = ty * tileW + tx;
+            const int seg = t * BIN_CHUNKS + chunk;
+            const int pos = __ldg(&tileOffsets[t]) + __ldg(&segOff[seg]) + atomicAdd(&segCursor[seg], 1);
             if (pos < isectCap)
                 flatten[pos] = g;
         }
 }
 
-// per tile: order the scattered ids ascending (= the order of the reference's stable sort by tile id)
+// per tile: order the ids of every (tile, chunk) segment ascending; consumes (zeroes) the segment cursors
 constexpr int SORT_SMEM = 4096;
-__global__ void __launch_bounds__(256) k_sort_tiles(const int *__restrict__ tileOffsets, const int *__restrict__ flatten, int *flattenSorted)
+constexpr int SORT_SEG_MAX = 256; // longer segments: sort the whole tile list cooperatively instead
+__global__ void __launch_bounds__(256) k_sort_tiles(const int *__restrict__ tileOffsets, const int *__restrict__ segOff, int *segLen,
+                                                     const int *__restrict__ flatten, int *flattenSorted)
 {
     __shared__ int s[SORT_SMEM];
+    __shared__ int sLen[BIN_CHUNKS], sOff[BIN_CHUNKS];
+    __shared__ int sMaxLen;
     const int t = blockIdx.x;
     const int start = tileOffsets[t], L = tileOffsets[t + 1] - start;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0)
+        sMaxLen = 0;
+    __syncthreads();
+    if (tid < BIN_CHUNKS)
+    {
+        const int off = segOff[(size_t)t * BIN_CHUNKS + tid];
+        int len = segLen[(size_t)t * BIN_CHUNKS + tid];
+        segLen[(size_t)t * BIN_CHUNKS + tid] = 0;
+        len = max(0, min(len, L - off)); // only differs when the intersection capacity overflowed
+        sLen[tid] = len, sOff[tid] = off;
+        if (len > SORT_SEG_MAX)
+            atomicMax(&sMaxLen, len);
+    }
     if (L <= 0)
         return;
-    const int tid = threadIdx.x;
-    if (L == 1)
+    const bool inSmem = L <= SORT_SMEM;
+    if (inSmem)
+        for (int i = tid; i < L; i += 256)
+            s[i] = flatten[start + i];
+    __syncthreads();
+    if (sMaxLen == 0)
     {
-        if (tid == 0)
-            flattenSorted[start] = flatten[start];
+        const int *src = inSmem ? s : flatten + start;
+        for (int c = wid; c < BIN_CHUNKS; c += 8)
+        {
+            const int n = sLen[c], o = sOff[c];
+            if (n == 0)
+                continue;
+            if (n <= 32)
+            {
+                // one element per lane, rank by n broadcasts
+                const int a = lane < n ? src[o + lane] : 0x7fffffff;
+                int rank = 0;
+                for (int j = 0; j < n; j++)
+                    rank += (__shfl_sync(0xffffffffu, a, j) < a);
+                if (lane < n)
+                    flattenSorted[start + o + rank] = a;
+            }
+            else
+            {
+                for (int i = lane; i < n; i += 32)
+                {
+                    const int a = src[o + i];
+                    int rank = 0;
+                    for (int j = 0; j < n; j++)
+                        rank += (src[o + j] < a);
+                    flattenSorted[start + o + rank] = a;
+                }
+            }
+        }
         return;
     }
-    if (L <= SORT_SMEM)
+    // a very long segment: bitonic sort of the whole tile list (ascending ids = sorted segments in chunk order)
+    if (inSmem)
     {
         int n = 2;
         while (n < L)
             n <<= 1;
-        for (int i = tid; i < n; i += 256)
-            s[i] = (i < L) ? flatten[start + i] : 0x7fffffff;
+        for (int i = L + tid; i < n; i += 256)
+            s[i] = 0x7fffffff;
         __syncthreads();
         for (int k = 2; k <= n; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1)
@@ -313,7 +392,7 @@ __global__ void __launch_bounds__(256) k_sort_tiles(const int *__restrict__ tile
     }
     else
     {
-        // very long list (> SORT_SMEM splats on one 16x16 tile): rank sort straight from global memory; ids are unique
+        // > SORT_SMEM splats on one 16x16 tile: rank sort straight from global memory; ids are unique
         for (int i = tid; i < L; i += 256)
         {
             int a = flatten[start + i];
@@ -687,18 +766,20 @@ void project_sh_fwd(const ParamPtrs &p, const int *nDev, int nUpper, const CamPa
     if (nUpper <= 0)
         return;
     GS_COUNT_LAUNCHES(1);
-    k_project_sh<<<cdiv(nUpper, 128), 128, 0, st>>>(p, nDev, cam, recs, grads, bins.tileCount, tileW, tileH, bins.items, bins.itemCap,
-                                                    bins.counters, forBackward ? 1 : 0);
+    k_project_sh<<<cdiv(nUpper, 128), 128, 0, st>>>(p, nDev, cam, recs, grads, bins.segCount, bin_chunk_size(nUpper), tileW, tileH, bins.items,
+                                                    bins.itemCap, bins.counters, forBackward ? 1 : 0);
 }
 
 void bin_tiles(const SplatRec *recs, const int *nDev, int nUpper, const Bins &bins, int tileW, int tileH, cudaStream_t st)
 {
     const int T = tileW * tileH;
-    GS_COUNT_LAUNCHES(3);
-    k_scan_tiles<<<1, 1024, 0, st>>>(bins.tileCount, bins.tileOffsets, bins.tileCursor, T, bins.isectCap, bins.counters);
+    GS_COUNT_LAUNCHES(4);
+    k_seg_scan<<<cdiv(T, 8), 256, 0, st>>>(bins.segCount, bins.segOff, bins.tileCount, T);
+    k_scan_tiles<<<1, 1024, 0, st>>>(bins.tileCount, bins.tileOffsets, T, bins.isectCap, bins.counters);
     if (nUpper > 0)
-        k_scatter_tiles<<<cdiv(nUpper, 256), 256, 0, st>>>(recs, nDev, bins.tileOffsets, bins.tileCursor, bins.flatten, bins.isectCap, tileW, tileH);
-    k_sort_tiles<<<T, 256, 0, st>>>(bins.tileOffsets, bins.flatten, bins.flattenSorted);
+        k_scatter_tiles<<<cdiv(nUpper, 256), 256, 0, st>>>(recs, nDev, bins.tileOffsets, bins.segOff, bins.segCount, bin_chunk_size(nUpper),
+                                                           bins.flatten, bins.isectCap, tileW, tileH);
+    k_sort_tiles<<<T, 256, 0, st>>>(bins.tileOffsets, bins.segOff, bins.segCount, bins.flatten, bins.flattenSorted);
 }
 
 void bwd_params_adam(const ParamPtrs &p, const ParamPtrs &m, const ParamPtrs &v, unsigned char *touched, const AdamStep &step, const int *nDev,

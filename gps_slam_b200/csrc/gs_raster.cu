@@ -18,6 +18,14 @@
 namespace gs
 {
 
+// 2^x by one MUFU.EX2 (flush-to-zero; inputs here are <= 0 or rejected right after)
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 constexpr int RB = 256; // splats per staged batch = threads per tile CTA
 
 template <int MODE>
@@ -44,6 +52,8 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
     float rdRaw = inside ? __ldg(&io.refDepth[pix]) : 0.f;
     float rd = (io.clampRef && rdRaw < 0.01f) ? 1000.0f : rdRaw;
     const float cut = rd + io.deltaDepth;
+    if (MODE != RASTER_RENDER && inside)
+        io.cut[pix] = cut; // depth-test threshold per pixel, read back by the rasteriser backward
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, w = 0.f;
 
     for (int b = start; b < end; b += RB)
@@ -55,7 +65,8 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
             const SplatRec *r = recs + __ldg(&flattenSorted[idx]);
             const float4 q0 = __ldg(&r->q0), q1 = __ldg(&r->q1);
             s0[tid] = q0;
-            s1[tid] = q1;
+            // conic in log2 units (see k_raster_bwd): alpha = opacity * 2^-(A dx^2 + B dx dy + C dy^2)
+            s1[tid] = make_float4((0.5f * 1.4426950408889634f) * q1.x, 1.4426950408889634f * q1.y, (0.5f * 1.4426950408889634f) * q1.z, q1.w);
             s2[tid] = __ldg(&r->q2);
             float ex, ey;
             if (alpha_extent(q1.x, q1.y, q1.z, q0.z, ex, ey))
@@ -94,8 +105,8 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
                     continue;
                 const float4 xyo = s0[t];
                 const float dx = xyo.x - px, dy = xyo.y - py;
-                const float sigma = 0.5f * (c.x * dx * dx + c.z * dy * dy) + c.y * dx * dy;
-                const float alpha = fminf(0.999f, xyo.z * __expf(-sigma));
+                const float sigma = fmaf(dx, fmaf(c.y, dy, c.x * dx), (c.z * dy) * dy);
+                const float alpha = fminf(0.999f, xyo.z * ex2_approx(-sigma));
                 if (sigma < 0.f || alpha < 1.f / 255.f)
                     continue;
                 const float4 col = s2[t];
@@ -200,10 +211,11 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane)
     return w1 + __shfl_xor_sync(full, w1, 1);
 }
 
-__global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__ recs, const int4 *__restrict__ items, int *counters, int itemCap,
-                                                     int W, int H, const float *__restrict__ refDepth, int clampRef, float deltaDepth,
-                                                     const float4 *__restrict__ v_out, const float *__restrict__ v_depthImg,
-                                                     SplatGrad *__restrict__ grads)
+// HAS_VD: a depth-channel gradient image is supplied (depth_weight > 0; off in every release config)
+template <bool HAS_VD>
+__global__ void __launch_bounds__(256, 4) k_raster_bwd(const SplatRec *__restrict__ recs, const int4 *__restrict__ items, int *counters, int itemCap,
+                                                     int W, const float *__restrict__ cutImg, const float4 *__restrict__ v_out,
+                                                     const float *__restrict__ v_depthImg, SplatGrad *__restrict__ grads)
 {
     const int lane = threadIdx.x & 31;
     const int nItems = min(counters[CNT_ITEMS], itemCap);
@@ -227,62 +239,80 @@ __global__ void __launch_bounds__(256) k_raster_bwd(const SplatRec *__restrict__
         const int g = item.x;
         const float4 q0 = __ldg(&recs[g].q0), q1 = __ldg(&recs[g].q1), q2 = __ldg(&recs[g].q2);
         const float opac = q0.z;
+        // sigma in log2 units: alpha = opac * 2^-(A dx^2 + B dx dy + C dy^2)
+        const float A = (0.5f * 1.4426950408889634f) * q1.x, B = 1.4426950408889634f * q1.y, C = (0.5f * 1.4426950408889634f) * q1.z;
         // the pixel rectangle was computed once by the projection pass (bwd_rect)
         const int rx = item.z & 0xffff, ry = item.z >> 16, rw = item.w & 0xffff, rh = item.w >> 16;
         const int npix = rw * rh;
         const float inv_rw = 1.0f / (float)rw;
         const int p0 = item.y;
         const int p1 = min(p0 + BWD_PIXELS_PER_ITEM, npix);
+        // Each lane walks two pixel sequences, ids p0 + lane + 64 k and p0 + 32 + lane + 64 k, in rect-linear order.  Pixel centre
+        // (px, py) and image index are advanced incrementally: +64 ids = +q64 rows, +r64 columns with at most one wrap.
+        const int q64 = (int)(64.5f * inv_rw), r64 = 64 - q64 * rw; // exact: rw <= 200
+        const float r64f = (float)r64, q64f = (float)q64, rwf = (float)rw;
+        const float xEnd = (float)(rx + rw);                       // first pixel centre beyond the rect is xEnd + 0.5
+        const int dpix = q64 * W + r64, dwrap = W - rw;
+        float px[2], py[2];
+        int pix[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+        {
+            const int id = p0 + u * 32 + lane;
+            const int row = (int)(((float)id + 0.5f) * inv_rw); // exact for id < 2^16, rw <= 200
+            const int col = id - row * rw;
+            px[u] = (float)(rx + col) + 0.5f, py[u] = (float)(ry + row) + 0.5f;
+            pix[u] = (ry + row) * W + rx + col;
+        }
         // gradient sums; the conic / mean gradients are accumulated as moments of t = v_sigma over (dx, dy):
         // v_conic = (Sxx/2, Sxy, Syy/2), v_mean2d = (a Sx + b Sy, b Sx + c Sy)
         float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f, vo = 0.f;
         // two groups (64 box pixels) per step: their image reads are issued together, before either is consumed
-        for (int pb = p0; pb < p1; pb += 64)
+        for (int id0 = p0 + lane; id0 - lane < p1; id0 += 64)
         {
-            float dxs[2], dys[2], viss[2], alphas[2], rds[2], vdps[2];
+            float dxs[2], dys[2], viss[2], araw[2], cuts[2], vdps[2];
             float4 vos[2];
             bool oks[2];
 #pragma unroll
             for (int u = 0; u < 2; u++)
             {
-                const int id = pb + u * 32 + lane;
-                const int row = (int)(((float)id + 0.5f) * inv_rw); // exact for id < 2^16, rw <= 200
-                const int col = id - row * rw;
-                const int j = rx + col, i = ry + row;
-                bool ok = id < p1;
-                const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-                const float dx = q0.x - px, dy = q0.y - py;
-                const float sigma = 0.5f * (q1.x * dx * dx + q1.z * dy * dy) + q1.y * dx * dy;
-                const float vis = __expf(-sigma);
-                const float alpha = fminf(0.999f, opac * vis);
-                ok = ok && !(sigma < 0.f || alpha < 1.f / 255.f);
-                dxs[u] = dx, dys[u] = dy, viss[u] = vis, alphas[u] = alpha, oks[u] = ok;
-                rds[u] = 0.f, vdps[u] = 0.f, vos[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float dx = q0.x - px[u], dy = q0.y - py[u];
+                const float s2 = fmaf(dx, fmaf(B, dy, A * dx), (C * dy) * dy);
+                const float vis = ex2_approx(-s2);
+                const float ar = opac * vis;
+                const bool ok = (id0 + u * 32 < p1) && !(s2 < 0.f || fminf(0.999f, ar) < 1.f / 255.f);
+                dxs[u] = dx, dys[u] = dy, viss[u] = vis, araw[u] = ar, oks[u] = ok;
+                cuts[u] = -1e30f, vdps[u] = 0.f, vos[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok)
                 {
-                    const int pix = i * W + j;
-                    rds[u] = __ldg(&refDepth[pix]);
-                    vos[u] = __ldg(&v_out[pix]);
-                    if (v_depthImg)
-                        vdps[u] = __ldg(&v_depthImg[pix]);
+                    cuts[u] = __ldg(&cutImg[pix[u]]);
+                    vos[u] = __ldg(&v_out[pix[u]]);
+                    if (HAS_VD)
+                        vdps[u] = __ldg(&v_depthImg[pix[u]]);
                 }
+                // advance to the pixel 64 ids further
+                px[u] += r64f, py[u] += q64f, pix[u] += dpix;
+                if (px[u] > xEnd)
+                    px[u] -= rwf, py[u] += 1.0f, pix[u] += dwrap;
             }
 #pragma unroll
             for (int u = 0; u < 2; u++)
             {
-                float rd = rds[u];
-                if (clampRef && rd < 0.01f)
-                    rd = 1000.0f;
-                if (!oks[u] || q1.w > rd + deltaDepth)
+                if (!oks[u] || q1.w > cuts[u])
                     continue;
-                const float alpha = alphas[u], vis = viss[u], dx = dxs[u], dy = dys[u], vdp = vdps[u];
+                const float vis = viss[u], dx = dxs[u], dy = dys[u], vdp = vdps[u];
+                const float alpha = fminf(0.999f, araw[u]);
                 const float4 vo4 = vos[u];
                 vr += alpha * vo4.x;
                 vg += alpha * vo4.y;
                 vb += alpha * vo4.z;
-                vd += alpha * vdp;
-                const float v_alpha = q2.x * vo4.x + q2.y * vo4.y + q2.z * vo4.z + q1.w * vdp + vo4.w;
-                if (opac * vis <= 0.999f)
+                float v_alpha = q2.x * vo4.x + q2.y * vo4.y + q2.z * vo4.z + vo4.w;
+                if (HAS_VD)
+                {
+                    vd += alpha * vdp;
+                    v_alpha += q1.w * vdp;
+                }
+                if (araw[u] <= 0.999f)
                 {
                     const float qv = vis * v_alpha;
                     const float t = -opac * qv;
@@ -363,6 +393,7 @@ __global__ void __launch_bounds__(256) k_composite(const float *__restrict__ acc
     float lsum = 0.f;
     if (inside)
     {
+        io.cut[pix] = ((io.clampRef && rdRaw < 0.01f) ? 1000.0f : rdRaw) + io.deltaDepth;
         const float *gt = io.gt + (size_t)pix * 3;
         float d0 = r0 - __ldg(gt + 0), d1 = r1 - __ldg(gt + 1), d2 = r2 - __ldg(gt + 2);
         lsum = fabsf(d0) + fabsf(d1) + fabsf(d2);
@@ -416,8 +447,10 @@ void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const Rast
 {
     GS_COUNT_LAUNCHES(1);
     cudaMemsetAsync(bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), st);
-    k_raster_bwd<<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, H, io.refDepth, io.clampRef, io.deltaDepth, io.v_out,
-                                          v_depth, grads);
+    if (v_depth)
+        k_raster_bwd<true><<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, v_depth, grads);
+    else
+        k_raster_bwd<false><<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, nullptr, grads);
 }
 
 void composite(int mode, const float *acc5, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st)
