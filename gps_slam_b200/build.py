@@ -20,6 +20,7 @@ SOURCES = [
     ("gs_project.cu", ["-fmad=false"]),
     ("gs_raster.cu", []),
     ("gs_spawn.cu", ["-fmad=false"]),
+    ("gs_staged.cu", ["-fmad=false"]),
     ("gs_engine.cu", ["-fmad=false"]),
 ]
 

@@ -172,7 +172,9 @@ void staged_sh_fwd(int N, const float *dirs, const float *coeffs, const unsigned
 void staged_sh_bwd(int N, const float *dirs, const float *coeffs, const unsigned char *mask, const float *v_colors, float *v_coeffs, float *v_dirs,
                    cudaStream_t st);
 void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *opac, const int *radii, SplatRec *recs,
-                 SplatGrad *grads, const Bins &bins, int tileW, int tileH, int *tilesPerGauss, bool forBackward, cudaStream_t st);
+                 SplatGrad *grads, const Bins &bins, int tileW, int tileH, int W, int H, int *tilesPerGauss, bool countTiles, bool forBackward,
+                 cudaStream_t st);
+void staged_cut(int P, const float *refDepth, float delta, float *cut, cudaStream_t st);
 void staged_isect_ids(const Bins &bins, int T, long long *isectIds, cudaStream_t st);
 void staged_unpack_grads(int N, const SplatRec *recs, const SplatGrad *grads, float *v_means2d, float *v_conics, float *v_colors4, float *v_opac,
                          cudaStream_t st);

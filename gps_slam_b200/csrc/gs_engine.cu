@@ -561,6 +561,202 @@ extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
     return 0;
 }
 
+// ---- staged entry points: one per gsplat::*_tensor function of the GES path (C = 1), device pointers in and out, caller-owned outputs.
+// viewmat: row-major 4x4 world-to-camera, K: row-major 3x3 (the reference passes [1,4,4] / [1,3,3] tensors).
+static void make_camera_viewmat(const gsb_gs *e, const float *viewmat, const float *K, int clamp_radii, CamParams &c)
+{
+    for (int i = 0; i < 3; i++)
+    {
+        for (int j = 0; j < 3; j++)
+            c.R[i * 3 + j] = viewmat[i * 4 + j];
+        c.t[i] = viewmat[i * 4 + 3];
+        c.cam_pos[i] = 0.f; // view directions are an input of the staged SH functions
+    }
+    c.fx = K[0], c.fy = K[4], c.cx = K[2], c.cy = K[5];
+    c.W = e->W, c.H = e->H;
+    c.eps2d = e->cfg.eps2d, c.near_plane = e->cfg.near_plane, c.far_plane = e->cfg.far_plane, c.radius_clip = e->cfg.radius_clip;
+    c.max_radii = clamp_radii;
+    cam_limits(c);
+}
+
+static int check_n(const gsb_gs *e, int n)
+{
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "null engine");
+    if (n < 0 || n > e->cap)
+        return gs_set_error(__FILE__, __LINE__, "Gaussian count exceeds the engine capacity");
+    return 0;
+}
+
+extern "C" int gsb_gs_projection_fwd(gsb_gs_t *e, int n, const float *means, const float *quats, const float *scales, const float *viewmat,
+                                     const float *K, int clamp_radii, int *radii, float *means2d, float *depths, float *conics)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means || !quats || !scales || !viewmat || !K || !radii || !means2d || !depths || !conics)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    CamParams cam;
+    make_camera_viewmat(e, viewmat, K, clamp_radii, cam);
+    staged_project_fwd(n, means, quats, scales, cam, radii, means2d, depths, conics, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_projection_bwd(gsb_gs_t *e, int n, const float *means, const float *quats, const float *scales, const float *viewmat,
+                                     const float *K, const int *radii, const float *conics, const float *v_means2d, const float *v_depths,
+                                     const float *v_conics, float *v_means, float *v_quats, float *v_scales)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means || !quats || !scales || !viewmat || !K || !radii || !conics || !v_means2d || !v_depths || !v_conics || !v_means || !v_quats ||
+        !v_scales)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    CamParams cam;
+    make_camera_viewmat(e, viewmat, K, 0, cam);
+    staged_project_bwd(n, means, quats, scales, cam, radii, conics, v_means2d, v_depths, v_conics, v_means, v_quats, v_scales, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_sh_fwd(gsb_gs_t *e, int n, int degrees_to_use, const float *dirs, const float *coeffs, const unsigned char *masks,
+                             float *colors)
+{
+    if (check_n(e, n))
+        return 1;
+    if (degrees_to_use != 3)
+        return gs_set_error(__FILE__, __LINE__, "only SH degree 3 (16 bases) is built: the SLAM path never uses another (raw_gs_model.cpp:256)");
+    if (!dirs || !coeffs || !colors)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    staged_sh_fwd(n, dirs, coeffs, masks, colors, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_sh_bwd(gsb_gs_t *e, int n, int degrees_to_use, const float *dirs, const float *coeffs, const unsigned char *masks,
+                             const float *v_colors, float *v_coeffs, float *v_dirs)
+{
+    if (check_n(e, n))
+        return 1;
+    if (degrees_to_use != 3)
+        return gs_set_error(__FILE__, __LINE__, "only SH degree 3 (16 bases) is built");
+    if (!dirs || !coeffs || !v_colors || !v_coeffs)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    staged_sh_bwd(n, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_isect_tiles(gsb_gs_t *e, int n, const float *means2d, const int *radii, int *tiles_per_gauss, int *n_isects)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means2d || !radii || !n_isects)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    GS_CUDA_OK(cudaMemsetAsync(e->bins.segCount, 0, sizeof(int) * (size_t)e->T * BIN_CHUNKS, e->stream));
+    staged_pack(n, means2d, nullptr, nullptr, nullptr, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, tiles_per_gauss, true,
+                false, e->stream);
+    bin_tiles(e->recs, nullptr, n, e->bins, e->tileW, e->tileH, e->stream);
+    GS_CUDA_OK(cudaMemcpyAsync(e->hostInts, e->bins.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream)); // the reference synchronises here too (n_isects sizes the output tensors)
+    if (e->hostInts[CNT_OVERFLOW] & 1)
+        return gs_set_error(__FILE__, __LINE__, "intersection capacity exceeded (gsb_gs_config.isect_capacity)");
+    *n_isects = e->hostInts[CNT_ISECTS];
+    return 0;
+}
+
+extern "C" int gsb_gs_isect_fetch(gsb_gs_t *e, int n_isects, long long *isect_ids, int *flatten_ids, int *tile_offsets)
+{
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "null engine");
+    if (n_isects < 0 || n_isects > e->bins.isectCap)
+        return gs_set_error(__FILE__, __LINE__, "invalid n_isects");
+    if (isect_ids && n_isects)
+        staged_isect_ids(e->bins, e->T, isect_ids, e->stream);
+    if (flatten_ids && n_isects)
+        GS_CUDA_OK(cudaMemcpyAsync(flatten_ids, e->bins.flattenSorted, sizeof(int) * (size_t)n_isects, cudaMemcpyDeviceToDevice, e->stream));
+    if (tile_offsets)
+        GS_CUDA_OK(cudaMemcpyAsync(tile_offsets, e->bins.tileOffsets, sizeof(int) * (size_t)e->T, cudaMemcpyDeviceToDevice, e->stream));
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// bins supplied by the caller (tile_offsets [T], flatten_ids [n_isects]) -> engine-side Bins view
+static int staged_bins(gsb_gs *e, const int *tile_offsets, const int *flatten_ids, int n_isects, Bins &b)
+{
+    b = e->bins;
+    GS_CUDA_OK(cudaMemcpyAsync(e->bins.tileOffsets, tile_offsets, sizeof(int) * (size_t)e->T, cudaMemcpyDeviceToDevice, e->stream));
+    e->hostInts[0] = n_isects;
+    GS_CUDA_OK(cudaMemcpyAsync(e->bins.tileOffsets + e->T, e->hostInts, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream)); // hostInts is reused by later calls
+    b.flattenSorted = const_cast<int *>(flatten_ids);
+    return 0;
+}
+
+extern "C" int gsb_gs_rasterize_ges_fwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4,
+                                        const float *opacities, const float *ref_depth, float delta_depth, const int *tile_offsets,
+                                        const int *flatten_ids, int n_isects, float *render4, float *alphas)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means2d || !conics || !colors4 || !opacities || !ref_depth || !tile_offsets || (!flatten_ids && n_isects) || !render4 || !alphas)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    // radii are not an input of the reference's forward: any positive value marks the splat live (bins come from the caller)
+    Bins b;
+    if (staged_bins(e, tile_offsets, flatten_ids, n_isects, b))
+        return 1;
+    staged_pack(n, means2d, conics, colors4, opacities, nullptr, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, false,
+                e->stream);
+    RasterIO io = make_io(e, ref_depth, nullptr, nullptr);
+    io.deltaDepth = delta_depth;
+    io.clampRef = 0; // the caller passes ref_depth_clamped (src/raw_gs_model.cpp:207)
+    io.render4 = render4, io.alphas = alphas;
+    raster_fwd(RASTER_RAW, e->recs, b, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_rasterize_ges_bwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4,
+                                        const float *opacities, const int *radii, const float *ref_depth, float delta_depth,
+                                        const float *v_render4, const float *v_alphas, float *v_means2d, float *v_conics, float *v_colors4,
+                                        float *v_opacities)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means2d || !conics || !colors4 || !opacities || !radii || !ref_depth || !v_render4 || !v_alphas || !v_means2d || !v_conics ||
+        !v_colors4 || !v_opacities)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    const int P = e->W * e->H;
+    GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
+    staged_pack(n, means2d, conics, colors4, opacities, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, true,
+                e->stream);
+    pack_v_out(P, v_render4, v_alphas, e->v_out, e->v_depth, e->stream);
+    staged_cut(P, ref_depth, delta_depth, e->cutImg, e->stream);
+    RasterIO io = make_io(e, ref_depth, nullptr, nullptr);
+    io.deltaDepth = delta_depth, io.clampRef = 0;
+    raster_bwd(e->recs, e->bins, e->W, e->H, io, e->v_depth, e->grads, e->stream);
+    staged_unpack_grads(n, e->recs, e->grads, v_means2d, v_conics, v_colors4, v_opacities, e->stream);
+    GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_adam_step(gsb_gs_t *e, long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr,
+                                float beta1, float beta2, float eps, int step)
+{
+    if (!e || !param || !grad || !exp_avg || !exp_avg_sq)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    if (n < 0 || n > 0x7fffffffLL || step < 1)
+        return gs_set_error(__FILE__, __LINE__, "invalid size or step");
+    const double b1 = (double)beta1, b2 = (double)beta2;
+    const double bc1 = 1.0 - pow(b1, step), bc2 = 1.0 - pow(b2, step);
+    AdamScalars a;
+    a.beta1 = beta1, a.beta2 = beta2, a.one_m_beta1 = (float)(1.0 - b1), a.one_m_beta2 = (float)(1.0 - b2);
+    a.sqrt_bc2 = (float)sqrt(bc2), a.eps = eps;
+    staged_adam((int)n, param, grad, exp_avg, exp_avg_sq, a, (float)((double)lr / bc1), e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ---- multi-GPU: the Gaussian set is sharded across ranks.  The GES blend is an order-independent sum, so each
 // rank rasterises its own Gaussians over the whole image into partial sums acc5 = render_colors [H*W*4] + alphas [H*W]; the
 // caller all-reduces acc5 (NCCL) and every rank finishes redundantly on the summed image.  Backward and Adam are rank-local.

@@ -275,10 +275,10 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const int *tileCount, int *
 
 __global__ void __launch_bounds__(256) k_scatter_tiles(const SplatRec *__restrict__ recs, const int *__restrict__ nDev,
                                                         const int *__restrict__ tileOffsets, const int *__restrict__ segOff, int *segCursor,
-                                                        int chunkSize, int *flatten, int isectCap, int tileW, int tileH)
+                                                        int chunkSize, int *flatten, int isectCap, int tileW, int tileH, int nUpper)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= *nDev)
+    if (g >= (nDev ? *nDev : nUpper)) // nDev == nullptr: staged call, the count is the launch bound itself
         return;
     float4 q0 = __ldg(&recs[g].q0);
     int radius = __float_as_int(q0.w);
@@ -778,7 +778,7 @@ void bin_tiles(const SplatRec *recs, const int *nDev, int nUpper, const Bins &bi
     k_scan_tiles<<<1, 1024, 0, st>>>(bins.tileCount, bins.tileOffsets, T, bins.isectCap, bins.counters);
     if (nUpper > 0)
         k_scatter_tiles<<<cdiv(nUpper, 256), 256, 0, st>>>(recs, nDev, bins.tileOffsets, bins.segOff, bins.segCount, bin_chunk_size(nUpper),
-                                                           bins.flatten, bins.isectCap, tileW, tileH);
+                                                           bins.flatten, bins.isectCap, tileW, tileH, nUpper);
     k_sort_tiles<<<T, 256, 0, st>>>(bins.tileOffsets, bins.segOff, bins.segCount, bins.flatten, bins.flattenSorted);
 }
 

@@ -211,6 +211,50 @@ int gsb_gs_render_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *b
 int gsb_gs_train_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *base_color_dev, const float *gt_rgb_dev,
                         const float *acc5_dev);
 
+/* ---- Staged entry points: one per gsplat::*_tensor function that RawGaussianModel::gesForward reaches through the autograd
+ * wrappers of gsplat/gsplat_wapper.hpp, so that each wrapper can be re-pointed at this library on its own.
+ * One camera (C = 1: the reference unsqueezes a camera dimension of size 1 everywhere, src/raw_gs_model.cpp:187); every pointer
+ * is DEVICE memory, fp32 / int32 contiguous, outputs are caller-allocated (the shim allocates them as torch tensors); calls are
+ * asynchronous on the engine's stream except gsb_gs_isect_tiles.  n <= gsb_gs_config.capacity.  viewmat row-major [4,4], K [3,3].
+ *   gsb_gs_projection_fwd     gsplat::fully_fused_projection_fwd_tensor (rasterizer/fully_fused_projection_fwd.cu:196-273; pinhole,
+ *                             quats+scales form, eps2d/near/far/radius_clip from the engine config); clamp_radii > 0 additionally applies
+ *                             torch::clamp_max(radii, max_gs_radii) (src/raw_gs_model.cpp:241-242).  Culled Gaussians: radii 0, rest 0.
+ *   gsb_gs_projection_bwd     gsplat::fully_fused_projection_bwd_tensor (fully_fused_projection_bwd.cu:288-403): v_means [n,3],
+ *                             v_quats [n,4], v_scales [n,3] (w.r.t. the real scales), written (not accumulated).
+ *   gsb_gs_sh_fwd / _bwd      gsplat::compute_sh_fwd_tensor / compute_sh_bwd_tensor (compute_sh_fwd.cu:40-72, compute_sh_bwd.cu:56-123):
+ *                             dirs [n,3] (not normalised), coeffs [n,16,3], masks uint8 [n] or NULL -> colors [n,3];
+ *                             v_coeffs [n,16,3], v_dirs [n,3] or NULL.  degrees_to_use must be 3.
+ *   gsb_gs_isect_tiles        gsplat::isect_tiles_tensor_no_depth + isect_offset_encode_tensor_no_depth (isect_tiles_no_depth.cu:132-461):
+ *                             bins the splats, returns n_isects (synchronises, as the reference does to size its tensors);
+ *                             tiles_per_gauss [n] optional.  gsb_gs_isect_fetch then copies isect_ids int64 [n_isects] (= tile index),
+ *                             flatten_ids int32 [n_isects] and tile_offsets int32 [tile_h*tile_w]; any of the three may be NULL.
+ *                             The reference's group_gs_ids / group_starts tables (work list of ITS backward) have no counterpart:
+ *                             the backward here derives its own work items.
+ *   gsb_gs_rasterize_ges_fwd  gsplat::rasterize_to_pixels_fwd_ges_tensor (rasterize_to_pixels_fwd_ges.cu:338-407): colors4 [n,4] = rgb +
+ *                             camera depth, opacities [n], ref_depth [H,W] ALREADY clamped by the caller -> render4 [H,W,4], alphas [H,W].
+ *   gsb_gs_rasterize_ges_bwd  gsplat::rasterize_to_pixels_bwd_ges_gs_parallel_tensor (rasterize_to_pixels_bwd_ges_new_parallel.cu:304-385):
+ *                             v_render4 [H,W,4], v_alphas [H,W] -> v_means2d [n,2], v_conics [n,3], v_colors4 [n,4], v_opacities [n].
+ *   gsb_gs_adam_step          torch::optim::Adam::step for one parameter tensor of n floats (no weight decay / amsgrad;
+ *                             src/raw_gs_model.cpp:661-672), step = 1-based count after increment. */
+int gsb_gs_projection_fwd(gsb_gs_t *e, int n, const float *means, const float *quats, const float *scales, const float *viewmat,
+                          const float *K, int clamp_radii, int *radii, float *means2d, float *depths, float *conics);
+int gsb_gs_projection_bwd(gsb_gs_t *e, int n, const float *means, const float *quats, const float *scales, const float *viewmat,
+                          const float *K, const int *radii, const float *conics, const float *v_means2d, const float *v_depths,
+                          const float *v_conics, float *v_means, float *v_quats, float *v_scales);
+int gsb_gs_sh_fwd(gsb_gs_t *e, int n, int degrees_to_use, const float *dirs, const float *coeffs, const unsigned char *masks, float *colors);
+int gsb_gs_sh_bwd(gsb_gs_t *e, int n, int degrees_to_use, const float *dirs, const float *coeffs, const unsigned char *masks,
+                  const float *v_colors, float *v_coeffs, float *v_dirs);
+int gsb_gs_isect_tiles(gsb_gs_t *e, int n, const float *means2d, const int *radii, int *tiles_per_gauss, int *n_isects);
+int gsb_gs_isect_fetch(gsb_gs_t *e, int n_isects, long long *isect_ids, int *flatten_ids, int *tile_offsets);
+int gsb_gs_rasterize_ges_fwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4, const float *opacities,
+                             const float *ref_depth, float delta_depth, const int *tile_offsets, const int *flatten_ids, int n_isects,
+                             float *render4, float *alphas);
+int gsb_gs_rasterize_ges_bwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4, const float *opacities,
+                             const int *radii, const float *ref_depth, float delta_depth, const float *v_render4, const float *v_alphas,
+                             float *v_means2d, float *v_conics, float *v_colors4, float *v_opacities);
+int gsb_gs_adam_step(gsb_gs_t *e, long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr, float beta1,
+                     float beta2, float eps, int step);
+
 /* state read-back for parity tests (synchronises) */
 enum
 {
