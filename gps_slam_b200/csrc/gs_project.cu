@@ -19,6 +19,7 @@
 //                     (src/raw_gs_model.cpp:654-705) in one pass over parameters and optimiser state.
 #include "common.cuh"
 #include "gs.h"
+#include "tma.cuh"
 
 namespace gs
 {
@@ -59,7 +60,23 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool inRange = g < *nDev;
+    const int nGauss = *nDev;
+    const bool inRange = g < nGauss;
+    // The 15x3 higher-order SH coefficients of the warp's 32 consecutive Gaussians are one contiguous 5,760-byte run: one TMA bulk
+    // copy per warp brings it into shared memory while the projection math below runs; lanes then read their own row at stride 45
+    // (odd -> conflict free).  Buffers are padded to a multiple of 128 Gaussians, so the full run is always readable.
+    __shared__ __align__(128) float sRest[4][32 * 45];
+    __shared__ unsigned long long sBar[4];
+    float *rest = sRest[threadIdx.x >> 5];
+    unsigned long long *bar = &sBar[threadIdx.x >> 5];
+    const bool warpLive = (g - lane) < nGauss;
+    if (lane == 0 && warpLive)
+    {
+        tma::mbar_init(bar, 1);
+        tma::mbar_expect_tx(bar, 32 * 45 * 4);
+        tma::load_1d(rest, p.rest + (size_t)(g - lane) * 45, 32 * 45 * 4, bar);
+    }
+    __syncwarp();
     Proj o;
     o.radius = 0;
     float mean[3];
@@ -74,19 +91,8 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
     const bool vis = o.radius > 0;
     const unsigned full = 0xffffffffu;
     const unsigned vm = __ballot_sync(full, vis);
-    // the 15x3 higher-order SH coefficients of the warp's 32 consecutive Gaussians are one contiguous 5,760-byte run: stage it in
-    // shared memory with coalesced loads; lanes then read their own row at stride 45 (odd -> conflict free)
-    __shared__ float sRest[4][32 * 45];
-    float *rest = sRest[threadIdx.x >> 5];
-    if (vm)
-    {
-        const int g0 = g - lane;
-        const int nRest = min(32, *nDev - g0) * 45;
-        const float *src = p.rest + (size_t)g0 * 45;
-        for (int i = lane; i < nRest; i += 32)
-            rest[i] = src[i];
-    }
-    __syncwarp();
+    if (warpLive)
+        tma::mbar_wait(bar, 0); // always, also when nothing is visible: the CTA must not retire with a copy in flight
     int nItems = 0, rectXY = 0, rectWH = 0;
     int bits = 0;
     float col[3] = {0.f, 0.f, 0.f};
@@ -428,7 +434,8 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
                                                                    const SplatRec *__restrict__ recs, const SplatGrad *__restrict__ grads,
                                                                    float4 *__restrict__ aux, ParamPtrs dbg, int haveDbg, int *counters)
 {
-    __shared__ float sRest[ADAM_WARPS][32 * 45];
+    __shared__ __align__(128) float sRest[ADAM_WARPS][32 * 45];
+    __shared__ unsigned long long sBar[ADAM_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g0 = (blockIdx.x * ADAM_WARPS + wid) * 32;
     const int g = g0 + lane;
@@ -437,6 +444,14 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     const int N = *nDev;
     if (g0 >= N)
         return;
+    // SH coefficient run of the warp's 32 Gaussians by one TMA bulk copy, overlapped with the record / gradient loads below
+    if (lane == 0)
+    {
+        tma::mbar_init(&sBar[wid], 1);
+        tma::mbar_expect_tx(&sBar[wid], 32 * 45 * 4);
+        tma::load_1d(sRest[wid], p.rest + (size_t)g0 * 45, 32 * 45 * 4, &sBar[wid]);
+    }
+    __syncwarp();
     const bool inRange = g < N;
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (inRange)
@@ -447,14 +462,9 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     const unsigned full = 0xffffffffu;
     const unsigned visMask = __ballot_sync(full, vis);
     float *rest = sRest[wid];
-    if (visMask)
-    {
-        const int nRest4 = min(32, N - g0) * 45 / 4 + 1; // buffers are padded to a multiple of 128 Gaussians
-        const float4 *src = reinterpret_cast<const float4 *>(p.rest + (size_t)g0 * 45);
-        for (int i = lane; i < min(nRest4, 360); i += 32)
-            reinterpret_cast<float4 *>(rest)[i] = src[i];
-    }
-    __syncwarp();
+    (void)visMask;
+    if (!vis)
+        tma::mbar_wait(&sBar[wid], 0); // every lane waits (the CTA must not retire with the copy in flight); visible lanes wait below
     float gm[3] = {0.f, 0.f, 0.f}, gsc[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gdc[3] = {0.f, 0.f, 0.f}, gop = 0.f;
     float basis[16], vcol[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -479,6 +489,7 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
         sh_basis(dir, sb);
         float cl[48];
         cl[0] = p.dc[g * 3 + 0], cl[1] = p.dc[g * 3 + 1], cl[2] = p.dc[g * 3 + 2];
+        tma::mbar_wait(&sBar[wid], 0);
 #pragma unroll
         for (int i = 0; i < 45; i++)
             cl[3 + i] = rest[lane * 45 + i];

@@ -26,13 +26,21 @@ __device__ __forceinline__ float ex2_approx(float x)
     return y;
 }
 
+#ifndef BWD_PREFETCH_CURSOR
+#define BWD_PREFETCH_CURSOR 0
+#endif
+#ifndef BWD_GRID_MULT
+#define BWD_GRID_MULT 1
+#endif
 constexpr int RB = 256; // splats per staged batch = threads per tile CTA
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__ recs, const int *__restrict__ tileOffsets,
+__global__ void __launch_bounds__(256, 6) k_raster_fwd(const SplatRec *__restrict__ recs, const int *__restrict__ tileOffsets,
                                                      const int *__restrict__ flattenSorted, int W, int H, int tileW, RasterIO io, float invCount)
 {
-    __shared__ float4 s0[RB], s1[RB], s2[RB], s3[RB];
+    // one array, four planes (mean/opacity | log2-conic/depth | colour | alpha-extent box): a single base register addresses all of them
+    __shared__ float4 sAll[4 * RB];
+    float4 *const s0 = sAll, *const s1 = sAll + RB, *const s2 = sAll + 2 * RB, *const s3 = sAll + 3 * RB;
     __shared__ unsigned char wlist[8][RB]; // per warp: batch slots whose alpha extent touches the warp's rectangle, ascending
     __shared__ float warpLoss[8];
     const int tile = blockIdx.x;
@@ -99,17 +107,16 @@ __global__ void __launch_bounds__(256) k_raster_fwd(const SplatRec *__restrict__
         {
             for (int q = 0; q < ns; q++)
             {
-                const int t = wlist[wid][q];
-                const float4 c = s1[t];
-                if (c.w > cut)
-                    continue;
-                const float4 xyo = s0[t];
+                const float4 *rec = sAll + wlist[wid][q];
+                const float4 c = rec[RB];
+                const float4 xyo = rec[0];
                 const float dx = xyo.x - px, dy = xyo.y - py;
                 const float sigma = fmaf(dx, fmaf(c.y, dy, c.x * dx), (c.z * dy) * dy);
                 const float alpha = fminf(0.999f, xyo.z * ex2_approx(-sigma));
-                if (sigma < 0.f || alpha < 1.f / 255.f)
+                // (the depth cut rejects well under 1% of the candidates: folded into the one branch)
+                if (sigma < 0.f || alpha < 1.f / 255.f || c.w > cut)
                     continue;
-                const float4 col = s2[t];
+                const float4 col = rec[2 * RB];
                 a0 += col.x * alpha;
                 a1 += col.y * alpha;
                 a2 += col.z * alpha;
@@ -211,31 +218,81 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane)
     return w1 + __shfl_xor_sync(full, w1, 1);
 }
 
-// HAS_VD: a depth-channel gradient image is supplied (depth_weight > 0; off in every release config)
-template <bool HAS_VD>
-__global__ void __launch_bounds__(256, 4) k_raster_bwd(const SplatRec *__restrict__ recs, const int4 *__restrict__ items, int *counters, int itemCap,
-                                                     int W, const float *__restrict__ cutImg, const float4 *__restrict__ v_out,
-                                                     const float *__restrict__ v_depthImg, SplatGrad *__restrict__ grads)
+// Sum 16 per-lane values over each HALF warp (lanes 0-15 and 16-31 independently) with 15 shuffles: at each halving step a lane
+// keeps one half of its values and hands the other half to its partner.  Returns, in lane l, the half-warp total of slot l & 15.
+__device__ __forceinline__ float halfwarp_reduce16(float (&v)[16], int lane)
 {
-    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    float w8[8], w4[4], w2[2];
+    const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        float send = h8 ? v[i] : v[i + 8], keep = h8 ? v[i + 8] : v[i];
+        w8[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        float send = h4 ? w8[i] : w8[i + 4], keep = h4 ? w8[i + 4] : w8[i];
+        w4[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+    {
+        float send = h2 ? w4[i] : w4[i + 2], keep = h2 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    float send = h1 ? w2[0] : w2[1], keep = h1 ? w2[1] : w2[0];
+    return keep + __shfl_xor_sync(full, send, 1);
+}
+
+// Rasteriser backward.  A HALF warp owns one work item (one splat, <= 2048 pixels of its rectangle): the two halves of a warp walk
+// two items side by side, 2 x 16 rect-linear pixels per step each, keep the 10 gradient sums in registers and finish with one
+// half-warp reduction and one store (or 10 atomics when the splat has several items).  Compared with a whole warp per item this
+// halves the per-item overhead (record loads, rectangle setup, reduction) and wastes fewer lanes on the typical 100-200 pixel
+// rectangles.  HAS_VD: a depth-channel gradient image is supplied (depth_weight > 0; off in every release config).
+template <bool HAS_VD>
+__global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restrict__ recs, const int4 *__restrict__ items, int *counters, int itemCap,
+                                                        int W, const float *__restrict__ cutImg, const float4 *__restrict__ v_out,
+                                                        const float *__restrict__ v_depthImg, SplatGrad *__restrict__ grads)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
     const int nItems = min(counters[CNT_ITEMS], itemCap);
     // dynamic distribution of work items over the resident warps: items differ by up to 64x in cost
     int *cursor = counters + CNT_BWD_CURSOR;
     constexpr int GRAB = 8; // consecutive items per cursor bump (same-address atomics are the scarce resource)
     int it = 0, itEnd = 0;
+    // the cursor bump for the NEXT batch is issued when a batch starts, so that its round trip to L2 is hidden behind the batch
+    int nextBatch = 0;
+#if BWD_PREFETCH_CURSOR
+    if (lane == 0)
+        nextBatch = atomicAdd(cursor, GRAB);
+#endif
     for (;;)
     {
         if (it >= itEnd)
         {
+#if BWD_PREFETCH_CURSOR
+            it = __shfl_sync(full, nextBatch, 0);
+#else
             if (lane == 0)
-                it = atomicAdd(cursor, GRAB);
-            it = __shfl_sync(0xffffffffu, it, 0);
+                nextBatch = atomicAdd(cursor, GRAB);
+            it = __shfl_sync(full, nextBatch, 0);
+#endif
             if (it >= nItems)
                 break;
             itEnd = min(it + GRAB, nItems);
+#if BWD_PREFETCH_CURSOR
+            if (lane == 0)
+                nextBatch = atomicAdd(cursor, GRAB);
+#endif
         }
-        const int4 item = __ldg(&items[it]);
-        it++;
+        const int mine = it + half;
+        const bool live = mine < itEnd;
+        it += 2;
+        const int4 item = __ldg(&items[live ? mine : itEnd - 1]);
         const int g = item.x;
         const float4 q0 = __ldg(&recs[g].q0), q1 = __ldg(&recs[g].q1), q2 = __ldg(&recs[g].q2);
         const float opac = q0.z;
@@ -246,62 +303,80 @@ __global__ void __launch_bounds__(256, 4) k_raster_bwd(const SplatRec *__restric
         const int npix = rw * rh;
         const float inv_rw = 1.0f / (float)rw;
         const int p0 = item.y;
-        const int p1 = min(p0 + BWD_PIXELS_PER_ITEM, npix);
-        // Each lane walks two pixel sequences, ids p0 + lane + 64 k and p0 + 32 + lane + 64 k, in rect-linear order.  Pixel centre
-        // (px, py) and image index are advanced incrementally: +64 ids = +q64 rows, +r64 columns with at most one wrap.
-        const int q64 = (int)(64.5f * inv_rw), r64 = 64 - q64 * rw; // exact: rw <= 200
-        const float r64f = (float)r64, q64f = (float)q64, rwf = (float)rw;
+        const int p1 = live ? min(p0 + BWD_PIXELS_PER_ITEM, npix) : p0;
+        // Each lane walks two pixel sequences, ids p0 + hl + 32 k and p0 + 16 + hl + 32 k, in rect-linear order.  Pixel centre
+        // (px, py) and image index are advanced incrementally: +32 ids = +q32 rows, +r32 columns with at most one wrap.
+        const int q32 = (int)(32.5f * inv_rw), r32 = 32 - q32 * rw; // exact: rw <= 200
+        const float r32f = (float)r32, q32f = (float)q32, rwf = (float)rw;
         const float xEnd = (float)(rx + rw);                       // first pixel centre beyond the rect is xEnd + 0.5
-        const int dpix = q64 * W + r64, dwrap = W - rw;
+        const int dpix = q32 * W + r32, dwrap = W - rw;
         float px[2], py[2];
         int pix[2];
 #pragma unroll
         for (int u = 0; u < 2; u++)
         {
-            const int id = p0 + u * 32 + lane;
+            const int id = p0 + u * 16 + hl;
             const int row = (int)(((float)id + 0.5f) * inv_rw); // exact for id < 2^16, rw <= 200
             const int col = id - row * rw;
             px[u] = (float)(rx + col) + 0.5f, py[u] = (float)(ry + row) + 0.5f;
             pix[u] = (ry + row) * W + rx + col;
         }
+        // steps of the longer of the two items
+        int steps = (p1 - p0 + 31) >> 5;
+        steps = max(steps, __shfl_xor_sync(full, steps, 16));
         // gradient sums; the conic / mean gradients are accumulated as moments of t = v_sigma over (dx, dy):
         // v_conic = (Sxx/2, Sxy, Syy/2), v_mean2d = (a Sx + b Sy, b Sx + c Sy)
         float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f, vo = 0.f;
-        // two groups (64 box pixels) per step: their image reads are issued together, before either is consumed
-        for (int id0 = p0 + lane; id0 - lane < p1; id0 += 64)
+        // Software pipeline: the image reads of step k+1 (depth cut + dL/d render, 20 B per pixel, L2 / L1 resident) are issued before
+        // the arithmetic of step k, unconditionally for every pixel of the rectangle, so that their latency is covered by a full step.
+        int id0 = p0 + hl;
+        float cutN[2], vdpN[2];
+        float4 voN[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
         {
-            float dxs[2], dys[2], viss[2], araw[2], cuts[2], vdps[2];
+            cutN[u] = -1e30f, vdpN[u] = 0.f, voN[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (id0 + u * 16 < p1)
+            {
+                cutN[u] = __ldg(&cutImg[pix[u]]);
+                voN[u] = __ldg(&v_out[pix[u]]);
+                if (HAS_VD)
+                    vdpN[u] = __ldg(&v_depthImg[pix[u]]);
+            }
+        }
+        for (int k = 0; k < steps; k++, id0 += 32)
+        {
+            float dxs[2], dys[2], cuts[2], vdps[2];
             float4 vos[2];
-            bool oks[2];
 #pragma unroll
             for (int u = 0; u < 2; u++)
             {
-                const float dx = q0.x - px[u], dy = q0.y - py[u];
-                const float s2 = fmaf(dx, fmaf(B, dy, A * dx), (C * dy) * dy);
-                const float vis = ex2_approx(-s2);
-                const float ar = opac * vis;
-                const bool ok = (id0 + u * 32 < p1) && !(s2 < 0.f || fminf(0.999f, ar) < 1.f / 255.f);
-                dxs[u] = dx, dys[u] = dy, viss[u] = vis, araw[u] = ar, oks[u] = ok;
-                cuts[u] = -1e30f, vdps[u] = 0.f, vos[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok)
-                {
-                    cuts[u] = __ldg(&cutImg[pix[u]]);
-                    vos[u] = __ldg(&v_out[pix[u]]);
-                    if (HAS_VD)
-                        vdps[u] = __ldg(&v_depthImg[pix[u]]);
-                }
-                // advance to the pixel 64 ids further
-                px[u] += r64f, py[u] += q64f, pix[u] += dpix;
+                dxs[u] = q0.x - px[u], dys[u] = q0.y - py[u];
+                cuts[u] = cutN[u], vdps[u] = vdpN[u], vos[u] = voN[u];
+                // advance to the pixel 32 ids further and start its reads
+                px[u] += r32f, py[u] += q32f, pix[u] += dpix;
                 if (px[u] > xEnd)
                     px[u] -= rwf, py[u] += 1.0f, pix[u] += dwrap;
+                cutN[u] = -1e30f;
+                if (id0 + 32 + u * 16 < p1)
+                {
+                    cutN[u] = __ldg(&cutImg[pix[u]]);
+                    voN[u] = __ldg(&v_out[pix[u]]);
+                    if (HAS_VD)
+                        vdpN[u] = __ldg(&v_depthImg[pix[u]]);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 2; u++)
             {
-                if (!oks[u] || q1.w > cuts[u])
+                const float dx = dxs[u], dy = dys[u], vdp = vdps[u];
+                const float s2 = fmaf(dx, fmaf(B, dy, A * dx), (C * dy) * dy);
+                const float vis = ex2_approx(-s2);
+                const float ar = opac * vis;
+                const float alpha = fminf(0.999f, ar);
+                // (pixels beyond the item carry cut = -1e30 and fail the depth test)
+                if (s2 < 0.f || alpha < 1.f / 255.f || q1.w > cuts[u])
                     continue;
-                const float vis = viss[u], dx = dxs[u], dy = dys[u], vdp = vdps[u];
-                const float alpha = fminf(0.999f, araw[u]);
                 const float4 vo4 = vos[u];
                 vr += alpha * vo4.x;
                 vg += alpha * vo4.y;
@@ -312,7 +387,7 @@ __global__ void __launch_bounds__(256, 4) k_raster_bwd(const SplatRec *__restric
                     vd += alpha * vdp;
                     v_alpha += q1.w * vdp;
                 }
-                if (araw[u] <= 0.999f)
+                if (ar <= 0.999f)
                 {
                     const float qv = vis * v_alpha;
                     const float t = -opac * qv;
@@ -332,16 +407,12 @@ __global__ void __launch_bounds__(256, 4) k_raster_bwd(const SplatRec *__restric
         v16[4] = 0.5f * sxx, v16[5] = sxy, v16[6] = 0.5f * syy, v16[7] = 0.f;
         v16[8] = vr, v16[9] = vg, v16[10] = vb, v16[11] = 0.f;
         v16[12] = v16[13] = v16[14] = v16[15] = 0.f;
-        const float total = warp_reduce16(v16, lane);
-        const int slot = lane >> 1;
-        if ((lane & 1) == 0 && slot < 12)
+        const float total = halfwarp_reduce16(v16, lane);
+        if (live && hl < 11 && hl != 7)
         {
-            float *f = reinterpret_cast<float *>(grads + g) + slot;
+            float *f = reinterpret_cast<float *>(grads + g) + hl;
             if (__float_as_int(q2.w) & 256)
-            {
-                if (slot != 7 && slot != 11)
-                    atomicAdd(f, total);
-            }
+                atomicAdd(f, total);
             else
                 *f = total;
         }
@@ -447,10 +518,31 @@ void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const Rast
 {
     GS_COUNT_LAUNCHES(1);
     cudaMemsetAsync(bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), st);
+    // persistent grid: exactly the resident CTAs (148 SMs x 3 per SM at 80 registers); work is handed out by the device-side cursor
+    static int ctasPerSm[2] = {0, 0};
+    const int v = v_depth ? 1 : 0;
+    if (!ctasPerSm[v])
+    {
+        int n = 0;
+        if (v)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster_bwd<true>, 256, 0);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster_bwd<false>, 256, 0);
+        ctasPerSm[v] = n > 0 ? n : 3;
+    }
+    static int sms = 0; // one process per GPU
+    if (!sms)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    const int grid = sms * ctasPerSm[v] * BWD_GRID_MULT;
     if (v_depth)
-        k_raster_bwd<true><<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, v_depth, grads);
+        k_raster_bwd<true><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, v_depth, grads);
     else
-        k_raster_bwd<false><<<148 * 8, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, nullptr, grads);
+        k_raster_bwd<false><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, nullptr, grads);
 }
 
 void composite(int mode, const float *acc5, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st)

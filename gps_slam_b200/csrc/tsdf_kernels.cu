@@ -838,9 +838,12 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
                                                   float4 invProj /* 1/fx 1/fy -cx -cy */, float oneOverVoxelSize, float mu,
                                                   const float2 *__restrict__ minmax, int mmW)
 {
-    // 8x32 pixel tiles keep a warp inside one row segment (coherent rays, coalesced 16-byte stores)
-    int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    // 32x8 pixel tile per CTA, one 8x4 pixel patch per warp: the 32 rays of a warp share one cell of the 1/8-resolution range
+    // image and march through the same few voxel blocks, so they take nearly the same number of steps (a warp runs for as long
+    // as its slowest ray) and their hash / voxel reads hit the same lines; each patch row is still one 128-byte store.
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
+    int y = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
     if (x >= W || y >= H)
         return;
     float2 mm = __ldg(&minmax[(x >> 3) + (y >> 3) * mmW]);

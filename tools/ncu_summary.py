@@ -23,14 +23,18 @@ WANT = [
     ("launch__block_size", "block"),
     ("launch__shared_mem_per_block_dynamic", "dyn_smem_B"),
     ("launch__shared_mem_per_block_static", "static_smem_B"),
-    ("smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "stall_long_scoreboard_pct"),
-    ("smsp__warp_issue_stalled_barrier_per_warp_active.pct", "stall_barrier_pct"),
-    ("smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "stall_math_throttle_pct"),
-    ("smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "stall_not_selected_pct"),
-    ("smsp__warp_issue_stalled_wait_per_warp_active.pct", "stall_wait_pct"),
-    ("smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "stall_short_scoreboard_pct"),
-    ("smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "stall_lg_throttle_pct"),
-    ("smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "stall_mio_throttle_pct"),
+    ("smsp__average_warp_latency_per_inst_issued.ratio", "warp_latency_per_inst"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_scoreboard"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_scoreboard"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math_throttle"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall_mio_throttle"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall_lg_throttle"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall_branch"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall_not_selected"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall_no_instruction"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall_dispatch"),
 ]
 
 
