@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -243,7 +243,7 @@ def main():
     intr, poses, rgba, depth = make_frames(n_frames, dev)
     rgba_h = torch.empty(rgba.shape, dtype=rgba.dtype, pin_memory=True).copy_(rgba)
     depth_h = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True).copy_(depth)
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("GSB_MAIN_STREAM_PRIORITY", "-1")))
     pipe = slam.SlamPipeline(intr, mode=mode, device=local, stream=stream, rank=rank, world=world, use_gt_pose=args.track == 0,
                              tracker=args.track or 1)
 

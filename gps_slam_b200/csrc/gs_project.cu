@@ -60,31 +60,36 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int nGauss = *nDev;
-    const bool inRange = g < nGauss;
     // The 15x3 higher-order SH coefficients of the warp's 32 consecutive Gaussians are one contiguous 5,760-byte run: one TMA bulk
     // copy per warp brings it into shared memory while the projection math below runs; lanes then read their own row at stride 45
-    // (odd -> conflict free).  Buffers are padded to a multiple of 128 Gaussians, so the full run is always readable.
+    // (odd -> conflict free).  Buffers are padded to a multiple of 128 Gaussians (and the grid never exceeds that), so the full run
+    // and every parameter below are readable for any g of the grid: all loads are requested before anything depends on them, the
+    // Gaussian count included.
     __shared__ __align__(128) float sRest[4][32 * 45];
     __shared__ unsigned long long sBar[4];
     float *rest = sRest[threadIdx.x >> 5];
     unsigned long long *bar = &sBar[threadIdx.x >> 5];
-    const bool warpLive = (g - lane) < nGauss;
-    if (lane == 0 && warpLive)
+    const bool warpLive = true;
+    if (lane == 0)
     {
         tma::mbar_init(bar, 1);
         tma::mbar_expect_tx(bar, 32 * 45 * 4);
         tma::load_1d(rest, p.rest + (size_t)(g - lane) * 45, 32 * 45 * 4, bar);
     }
+    float mean[3];
+    mean[0] = p.means[g * 3 + 0], mean[1] = p.means[g * 3 + 1], mean[2] = p.means[g * 3 + 2];
+    const float ls0 = p.scales[g * 3 + 0], ls1 = p.scales[g * 3 + 1], ls2 = p.scales[g * 3 + 2];
+    const float4 q4 = reinterpret_cast<const float4 *>(p.quats)[g];
+    const float opacLogit = p.opac[g];
+    const float dc0 = p.dc[g * 3 + 0], dc1 = p.dc[g * 3 + 1], dc2 = p.dc[g * 3 + 2];
+    const int nGauss = *nDev;
+    const bool inRange = g < nGauss;
     __syncwarp();
     Proj o;
     o.radius = 0;
-    float mean[3];
     if (inRange)
     {
-        mean[0] = p.means[g * 3 + 0], mean[1] = p.means[g * 3 + 1], mean[2] = p.means[g * 3 + 2];
-        float scale[3] = {expf(p.scales[g * 3 + 0]), expf(p.scales[g * 3 + 1]), expf(p.scales[g * 3 + 2])};
-        float4 q4 = reinterpret_cast<const float4 *>(p.quats)[g];
+        float scale[3] = {expf(ls0), expf(ls1), expf(ls2)};
         float quat[4] = {q4.x, q4.y, q4.z, q4.w};
         o = project_one(mean, quat, scale, cam, nullptr);
     }
@@ -99,13 +104,13 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
     float opac = 0.f;
     if (vis)
     {
-        opac = 1.0f / (1.0f + expf(-p.opac[g]));
+        opac = 1.0f / (1.0f + expf(-opacLogit));
         // SH colour (degree 3), dirs = means - camT, colour = max(SH + 0.5, 0)
         float dir[3] = {mean[0] - cam.cam_pos[0], mean[1] - cam.cam_pos[1], mean[2] - cam.cam_pos[2]};
         ShBasis sb;
         sh_basis(dir, sb);
         float cl[48];
-        cl[0] = p.dc[g * 3 + 0], cl[1] = p.dc[g * 3 + 1], cl[2] = p.dc[g * 3 + 2];
+        cl[0] = dc0, cl[1] = dc1, cl[2] = dc2;
 #pragma unroll
         for (int i = 0; i < 45; i++)
             cl[3 + i] = rest[lane * 45 + i];
@@ -293,15 +298,31 @@ __global__ void __launch_bounds__(256) k_scatter_tiles(const SplatRec *__restric
     int x0, y0, x1, y1;
     tile_rect(q0.x, q0.y, radius, tileW, tileH, x0, y0, x1, y1);
     const int chunk = g / chunkSize;
-    for (int ty = y0; ty < y1; ty++)
-        for (int tx = x0; tx < x1; tx++)
+    // The cursor bumps return a value (the slot), so each one costs a full round trip to L2.  They are independent: issue them four
+    // at a time and only then consume the results, instead of one round trip per tile.
+    constexpr int B = 4;
+    const int nx = x1 - x0, total = nx * (y1 - y0);
+    for (int base = 0; base < total; base += B)
+    {
+        int pos[B];
+#pragma unroll
+        for (int i = 0; i < B; i++)
         {
-            const int t = ty * tileW + tx;
-            const int seg = t * BIN_CHUNKS + chunk;
-            const int pos = __ldg(&tileOffsets[t]) + __ldg(&segOff[seg]) + atomicAdd(&segCursor[seg], 1);
-            if (pos < isectCap)
-                flatten[pos] = g;
+            const int k = base + i;
+            pos[i] = isectCap;
+            if (k < total)
+            {
+                const int row = k / nx;
+                const int t = (y0 + row) * tileW + x0 + (k - row * nx);
+                const int seg = t * BIN_CHUNKS + chunk;
+                pos[i] = __ldg(&tileOffsets[t]) + __ldg(&segOff[seg]) + atomicAdd(&segCursor[seg], 1);
+            }
         }
+#pragma unroll
+        for (int i = 0; i < B; i++)
+            if (pos[i] < isectCap)
+                flatten[pos[i]] = g;
+    }
 }
 
 // per tile: order the ids of every (tile, chunk) segment ascending; consumes (zeroes) the segment cursors
@@ -427,6 +448,7 @@ __device__ __forceinline__ void adam_one(float *p, float *m, float *v, size_t id
 //     state flag in an 80-byte aux record.
 //  k_adam_rest: pure streaming pass over the higher-order SH coefficients and their two moments (76% of all parameter bytes):
 //     16-byte accesses, two per thread in flight, gradient = basis[k] * v_colour[c] rebuilt from the aux record.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr int ADAM_WARPS = 4;
 constexpr int AUX_FLOATS = 20; // basis[1..15], vcol[3], flag, pad
 __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, ParamPtrs m, ParamPtrs v, unsigned char *touched, AdamStep step,
@@ -441,6 +463,15 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     const int g = g0 + lane;
     if (blockIdx.x == 0 && threadIdx.x == 0)
         counters[CNT_ITEMS] = 0; // re-arm for the next projection
+    // Everything whose address does not depend on data is requested up front (g < capacity: the grid covers nUpper <= capacity and
+    // buffers are padded to 128 Gaussians), so the kernel pays one memory round trip instead of four chained ones:
+    // record + raster gradients + state flag now, optimiser moments pulled into L2 for the Adam step at the end.
+    const float4 q0r = __ldg(&recs[g].q0), q1r = __ldg(&recs[g].q1), q2r = __ldg(&recs[g].q2);
+    const float4 sg0 = __ldg(&grads[g].g0), sg1 = __ldg(&grads[g].g1), sg2 = __ldg(&grads[g].g2);
+    const unsigned char tch = touched[g];
+    prefetch_l2(m.means + g * 3), prefetch_l2(v.means + g * 3), prefetch_l2(m.scales + g * 3), prefetch_l2(v.scales + g * 3);
+    prefetch_l2(m.dc + g * 3), prefetch_l2(v.dc + g * 3), prefetch_l2(m.quats + g * 4), prefetch_l2(v.quats + g * 4);
+    prefetch_l2(m.opac + g), prefetch_l2(v.opac + g);
     const int N = *nDev;
     if (g0 >= N)
         return;
@@ -453,12 +484,10 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     }
     __syncwarp();
     const bool inRange = g < N;
-    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inRange)
-        q0 = recs[g].q0;
+    const float4 q0 = inRange ? q0r : make_float4(0.f, 0.f, 0.f, 0.f);
     const int radius = __float_as_int(q0.w);
     const bool vis = inRange && radius > 0;
-    const bool had = inRange && touched[g] != 0;
+    const bool had = inRange && tch != 0;
     const unsigned full = 0xffffffffu;
     const unsigned visMask = __ballot_sync(full, vis);
     float *rest = sRest[wid];
@@ -472,8 +501,9 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
         basis[k] = 0.f;
     if (vis)
     {
-        float4 q1 = recs[g].q1, q2 = recs[g].q2;
-        SplatGrad sg = grads[g];
+        const float4 q1 = q1r, q2 = q2r;
+        SplatGrad sg;
+        sg.g0 = sg0, sg.g1 = sg1, sg.g2 = sg2;
         int bits = __float_as_int(q2.w);
         vcol[0] = (bits & 1) ? sg.g2.x : 0.f;
         vcol[1] = (bits & 2) ? sg.g2.y : 0.f;

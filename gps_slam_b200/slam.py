@@ -10,7 +10,9 @@ mode "train": TSDF fusion per frame and, every local_opt_interval frames, window
 torch is used for device buffers only; every computation is a kernel of libgpsslam_b200.so.
 """
 import collections
+import contextlib
 import math
+import os
 import random
 
 import numpy as np
@@ -55,23 +57,30 @@ def rot_compare(Ra, Rb):
 
 
 class BufferPool:
-    """device image buffers recycled between cycles (the reference allocates fresh tensors per raycast / camera)"""
+    """device image buffers recycled between cycles (the reference allocates fresh tensors per raycast / camera).  A buffer may be
+    released while work that reads it is still queued on another stream: put() takes the event after which it is free, and
+    get() makes the stream that is going to overwrite it wait for that event (device-side, the host never blocks)."""
 
     def __init__(self, device):
-        self.device, self.free = device, collections.defaultdict(list)
+        self.device, self.free = device, collections.defaultdict(collections.deque)
 
-    def get(self, shape):
+    def get(self, shape, writer_stream=None):
         f = self.free[shape]
-        return f.pop() if f else torch.empty(shape, dtype=torch.float32, device=self.device)
+        if not f:
+            return torch.empty(shape, dtype=torch.float32, device=self.device)
+        t, ev = f.popleft()
+        if ev is not None and writer_stream is not None:
+            writer_stream.wait_event(ev)
+        return t
 
-    def put(self, t):
+    def put(self, t, free_after=None):
         if t is not None:
-            self.free[tuple(t.shape)].append(t)
+            self.free[tuple(t.shape)].append((t, free_after))
 
 
 class SlamPipeline:
     def __init__(self, intr, mode="train", device=0, stream=None, rank=0, world=1, cfg=None, seed=42, gs_capacity=1 << 21, use_gt_pose=True,
-                 tracker=1):
+                 tracker=1, overlap=True):
         """use_gt_pose=False: online tracking (TSDF.use_gt_pose: false) with the extended (1) or icp (2) tracker.
         world > 1: Gaussians sharded across ranks (parallel.py); torch.distributed must be initialised by the caller."""
         self.intr, self.mode, self.rank, self.world = intr, mode, rank, world
@@ -85,11 +94,20 @@ class SlamPipeline:
         self.acc5 = torch.empty(self.W * self.H * 5, dtype=torch.float32, device=self.device) if (world > 1 and mode == "train") else None
         self.sp_rgb = self.sp_depth = self.sp_alpha = None
         self.gs = E.GaussianEngine(self.W, self.H, capacity=gs_capacity, device=device) if mode == "train" else None
-        self.stream = stream
-        if stream is not None:
-            self.tsdf.set_stream(stream.cuda_stream)
-            if self.gs:
-                self.gs.set_stream(stream.cuda_stream)
+        # Two streams (train mode): the TSDF side of the loop (fusion, raycasts, raycast -> tensor glue) runs on sT, the Gaussian side
+        # (spawn, optimiser iterations, prune) on sG.  Nothing on the TSDF side depends on the Gaussians, so the 20 optimiser
+        # iterations of a cycle (issue-bound rasteriser kernels) overlap with the fusion + raycasts of the following frames
+        # (latency-bound kernels); events order the hand-overs (maps -> optimiser, spawn -> next free-view raycast, buffer reuse).
+        # Results are identical to the single-stream order.  overlap=False keeps everything on one stream.
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.sG = self.stream
+        prio = int(os.environ.get("GSB_TSDF_STREAM_PRIORITY", "0"))   # 0 normal, -1 high (experiments; the Gaussian side is the critical path)
+        self.sT = torch.cuda.Stream(device=self.device, priority=prio) if (overlap and mode == "train") else self.sG
+        self.tsdf.set_stream(self.sT.cuda_stream or 1)
+        if self.gs:
+            self.gs.set_stream(self.sG.cuda_stream or 1)
+        self.ev_spawn = None       # recorded on sG after the spawn (the last reader of the engine's free-view vertex image)
+        self.ev_gs = None          # recorded on sG after the last enqueued Gaussian-side work that reads camera buffers / the free vertex image
         self.pool = BufferPool(self.device)
         if mode == "train":
             # image buffers are recycled; allocate the working set up front so that no cudaMalloc (a device-wide sync) lands inside
@@ -102,6 +120,8 @@ class SlamPipeline:
 
     # ------------------------------------------------------------------------------------------------------------
     def reset(self):
+        torch.cuda.synchronize(self.device)
+        self.ev_gs = self.ev_spawn = None
         self.tsdf.resetAll()
         if self.gs:
             self.gs.set_params(dict(means=np.zeros((0, 3), np.float32), scales=np.zeros((0, 3), np.float32), quats=np.zeros((0, 4), np.float32),
@@ -126,9 +146,44 @@ class SlamPipeline:
             self.gs.close()
 
     def _release(self, cam):
-        self.pool.put(cam.depth_map)
-        self.pool.put(cam.color_map)
+        self.pool.put(cam.depth_map, self.ev_gs)
+        self.pool.put(cam.color_map, self.ev_gs)
         cam.depth_map = cam.color_map = None
+
+    @contextlib.contextmanager
+    def _glue(self):
+        """the Gaussian engine's stateless image kernels (frame_to_float, raycast_maps) issued on the TSDF stream"""
+        if self.sT is self.sG:
+            yield
+            return
+        self.gs.set_stream(self.sT.cuda_stream or 1)
+        try:
+            yield
+        finally:
+            self.gs.set_stream(self.sG.cuda_stream or 1)
+
+    def _handover(self, src, dst):
+        """dst waits (on the device) for everything queued on src so far"""
+        if src is dst:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(src)
+        dst.wait_event(ev)
+        return ev
+
+    @contextlib.contextmanager
+    def single_stream(self):
+        """everything on the Gaussian stream (per-kernel timing, evaluation renders); synchronises on entry and exit"""
+        torch.cuda.synchronize(self.device)
+        keep = self.sT
+        self.sT = self.sG
+        self.tsdf.set_stream(self.sG.cuda_stream or 1)
+        try:
+            yield
+        finally:
+            torch.cuda.synchronize(self.device)
+            self.sT = keep
+            self.tsdf.set_stream(self.sT.cuda_stream or 1)
 
     # ------------------------------------------------------------------------------------------------------------
     def process_frame(self, idx, rgba_all, depth_all, poses, resident):
@@ -148,17 +203,27 @@ class SlamPipeline:
         self._update_frame_list(idx, c2w, est)
         c = self.cfg
         if idx % c["local_opt_interval"] == 0 and idx > 0:
+            if self.ev_spawn is not None and self.sT is not self.sG:
+                self.sT.wait_event(self.ev_spawn)    # the previous spawn has read the engine's free-view vertex image
             self._key_frame_raycast()
             self._local_frame_raycast()
+            self._handover(self.sT, self.sG)          # maps and camera images are ready for the Gaussian side
             self._init_new_gaussians()
+            if self.sT is not self.sG:
+                self.ev_spawn = torch.cuda.Event()
+                self.ev_spawn.record(self.sG)
             self._local_optimize()
             self._remove_redundant()
+            if self.sT is not self.sG:
+                self.ev_gs = torch.cuda.Event()
+                self.ev_gs.record(self.sG)
             self.cycles += 1
 
     def _make_cam(self, idx, c2w, est):
         """curr_cam.toGPU(): float image of the current frame (slam_pipeline.cpp:84)"""
-        img = self.pool.get((self.H, self.W, 3))
-        self.gs.frame_to_float(self.tsdf.current_rgba(), None, img, None)
+        img = self.pool.get((self.H, self.W, 3), self.sT)
+        with self._glue():
+            self.gs.frame_to_float(self.tsdf.current_rgba(), None, img, None)
         return Cam(idx, c2w, est, img)
 
     def _update_frame_list(self, idx, c2w, est):
@@ -174,7 +239,7 @@ class SlamPipeline:
                 old = self.window.popleft()
                 if not any(k is old for k in self.keyframes):
                     self._release(old)
-                    self.pool.put(old.image)
+                    self.pool.put(old.image, self.ev_gs)
         is_key = False
         if not self.keyframes:
             is_key = True
@@ -189,10 +254,13 @@ class SlamPipeline:
     def _raycast_by_cam(self, cam):
         """runRaycastByCam (slam_pipeline.cpp:362-415): free-view raycast at the engine's logged pose of that frame + tensor glue"""
         self.tsdf.runRaycast(syn.c2w_to_colmajor(cam.c2w_slam), self.intr)
-        if cam.depth_map is None:
-            cam.depth_map = self.pool.get((self.H, self.W))
-            cam.color_map = self.pool.get((self.H, self.W, 3))
-        self.gs.raycast_maps(self.tsdf.GetFreeVertex(), self.tsdf.GetFreeImage(), cam.c2w, self.tsdf.getVoxelSize(), cam.depth_map, cam.color_map)
+        # fresh map buffers every time: the previous cycle's optimiser iterations may still be reading the old ones on the other stream
+        self._release(cam)
+        cam.depth_map = self.pool.get((self.H, self.W), self.sT)
+        cam.color_map = self.pool.get((self.H, self.W, 3), self.sT)
+        with self._glue():
+            self.gs.raycast_maps(self.tsdf.GetFreeVertex(), self.tsdf.GetFreeImage(), cam.c2w, self.tsdf.getVoxelSize(), cam.depth_map,
+                                 cam.color_map)
 
     def _key_frame_raycast(self):
         """keyFrameRaycast, sample_method == "random" (slam_pipeline.cpp:528-561): up to keyframe_select_max keyframes drawn
@@ -271,6 +339,10 @@ class SlamPipeline:
 
     # ------------------------------------------------------------------------------------------------------------
     def end_of_step(self, resident):
+        # step boundary: each stream waits for the other (device-side), so that events recorded on the main stream bracket all the
+        # work of the step
+        self._handover(self.sT, self.sG)
+        self._handover(self.sG, self.sT)
         if not resident:
             # what a caller reads back after a cycle: the pose estimate and the last loss (slam_pipeline.cpp:81-82, progress bar :283)
             self.tsdf.sync()
@@ -281,9 +353,10 @@ class SlamPipeline:
     def render_eval(self, c2w, rgb, depth, alpha):
         """renderEvalImgs body for one camera (slam_pipeline.cpp:588-660): free-view raycast + gesForward"""
         cam = Cam(-1, np.asarray(c2w, np.float32), np.asarray(c2w, np.float32), None)
-        self._raycast_by_cam(cam)
-        self._forward_all(cam, rgb, depth, alpha)
-        base = cam.color_map.clone()
+        with self.single_stream():
+            self._raycast_by_cam(cam)
+            self._forward_all(cam, rgb, depth, alpha)
+            base = cam.color_map.clone()
         self._release(cam)
         return base
 
@@ -324,6 +397,10 @@ class SlamPipeline:
         return float(np.mean(ms)) * 1e-3
 
     def time_dominant_kernel(self, stream, peak_gbs, reps=20):
+        with self.single_stream():
+            return self._time_dominant_kernel(stream, peak_gbs, reps)
+
+    def _time_dominant_kernel(self, stream, peak_gbs, reps=20):
         """Per-kernel device times (CUDA events on the launching stream, L2 flushed by a 256 MiB fill between launches) and the
         roofline entry of the kernel BASELINE.json names: the rasteriser backward in train mode (algorithmic bytes
         24*P + 48*I + 80*N_vis), the TSDF integrate kernel in recon mode (V*(4+16+2*4096) + 8*P)."""
