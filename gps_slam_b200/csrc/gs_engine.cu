@@ -543,7 +543,10 @@ extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
         bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
         break;
     case 2: raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, e->lastIo, e->stream); break;
-    case 3: raster_bwd(e->recs, e->bins, e->W, e->H, e->lastIo, nullptr, e->grads, e->stream); break;
+    case 3:
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), e->stream));
+        raster_bwd(e->recs, e->bins, e->W, e->H, e->lastIo, nullptr, e->grads, e->stream);
+        break;
     case 4: GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream)); break;
     case 5: // parameter backward + Adam with a zero step size (moments advance, parameters do not move)
     {
@@ -727,6 +730,7 @@ extern "C" int gsb_gs_rasterize_ges_bwd(gsb_gs_t *e, int n, const float *means2d
         return gs_set_error(__FILE__, __LINE__, "null argument");
     const int P = e->W * e->H;
     GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
+    GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), e->stream));
     staged_pack(n, means2d, conics, colors4, opacities, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, true,
                 e->stream);
     pack_v_out(P, v_render4, v_alphas, e->v_out, e->v_depth, e->stream);

@@ -517,7 +517,7 @@ void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, 
 void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth, SplatGrad *grads, cudaStream_t st)
 {
     GS_COUNT_LAUNCHES(1);
-    cudaMemsetAsync(bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), st);
+    // (the work cursor CNT_BWD_CURSOR is zeroed by the binning pass of the same iteration, or by the staged entry point)
     // persistent grid: exactly the resident CTAs (148 SMs x 3 per SM at 80 registers); work is handed out by the device-side cursor
     static int ctasPerSm[2] = {0, 0};
     const int v = v_depth ? 1 : 0;
