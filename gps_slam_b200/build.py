@@ -21,6 +21,8 @@ SOURCES = [
     ("gs_raster.cu", []),
     ("gs_spawn.cu", ["-fmad=false"]),
     ("gs_staged.cu", ["-fmad=false"]),
+    ("gs_raw.cu", []),
+    ("gs_ssim.cu", []),
     ("gs_engine.cu", ["-fmad=false"]),
 ]
 

@@ -171,9 +171,9 @@ void staged_project_bwd(int N, const float *means, const float *quats, const flo
 void staged_sh_fwd(int N, const float *dirs, const float *coeffs, const unsigned char *mask, float *colors, cudaStream_t st);
 void staged_sh_bwd(int N, const float *dirs, const float *coeffs, const unsigned char *mask, const float *v_colors, float *v_coeffs, float *v_dirs,
                    cudaStream_t st);
-void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *opac, const int *radii, SplatRec *recs,
-                 SplatGrad *grads, const Bins &bins, int tileW, int tileH, int W, int H, int *tilesPerGauss, bool countTiles, bool forBackward,
-                 cudaStream_t st);
+void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *depths, const float *opac, const int *radii,
+                 SplatRec *recs, SplatGrad *grads, const Bins &bins, int tileW, int tileH, int W, int H, int *tilesPerGauss, bool countTiles,
+                 bool forBackward, cudaStream_t st);
 void staged_cut(int P, const float *refDepth, float delta, float *cut, cudaStream_t st);
 void staged_isect_ids(const Bins &bins, int T, long long *isectIds, cudaStream_t st);
 void staged_unpack_grads(int N, const SplatRec *recs, const SplatGrad *grads, float *v_means2d, float *v_conics, float *v_colors4, float *v_opac,
@@ -186,5 +186,18 @@ void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const Rast
                 SplatGrad *grads, cudaStream_t st);
 void composite(int mode, const float *acc5 /* [P*4] render then [P] alphas */, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
 void pack_v_out(int P, const float *v_render4, const float *v_alphas, float4 *v_out, float *v_depth, cudaStream_t st);
+
+// ---- gs_raw.cu: depth-sorted front-to-back compositing (render_method "raw")
+void sort_tiles_depth(const SplatRec *recs, const Bins &bins, int T, cudaStream_t st);
+void isect_ids_depth(const SplatRec *recs, const Bins &bins, int T, long long *isectIds, cudaStream_t st);
+void raw_fwd(const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const float *background, float *render4, float *alphas,
+             int *lastIds, cudaStream_t st);
+void raw_bwd(int N, const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const float *background, const float *alphas,
+             const int *lastIds, const float *v_render4, const float *v_alphas, SplatGrad *grads, cudaStream_t st);
+// ---- gs_ssim.cu
+void ssim_fwd(int planes, int H, int W, float C1, float C2, const float *img1, const float *img2, float *ssimMap, float *dm_dmu1,
+              float *dm_dsigma1_sq, float *dm_dsigma12, cudaStream_t st);
+void ssim_bwd(int planes, int H, int W, const float *img1, const float *img2, const float *dL_dmap, const float *dm_dmu1,
+              const float *dm_dsigma1_sq, const float *dm_dsigma12, float *dL_dimg1, cudaStream_t st);
 
 } // namespace gs

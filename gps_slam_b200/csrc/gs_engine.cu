@@ -656,7 +656,7 @@ extern "C" int gsb_gs_isect_tiles(gsb_gs_t *e, int n, const float *means2d, cons
     if (!means2d || !radii || !n_isects)
         return gs_set_error(__FILE__, __LINE__, "null argument");
     GS_CUDA_OK(cudaMemsetAsync(e->bins.segCount, 0, sizeof(int) * (size_t)e->T * BIN_CHUNKS, e->stream));
-    staged_pack(n, means2d, nullptr, nullptr, nullptr, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, tiles_per_gauss, true,
+    staged_pack(n, means2d, nullptr, nullptr, nullptr, nullptr, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, tiles_per_gauss, true,
                 false, e->stream);
     bin_tiles(e->recs, nullptr, n, e->bins, e->tileW, e->tileH, e->stream);
     GS_CUDA_OK(cudaMemcpyAsync(e->hostInts, e->bins.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -707,7 +707,7 @@ extern "C" int gsb_gs_rasterize_ges_fwd(gsb_gs_t *e, int n, const float *means2d
     Bins b;
     if (staged_bins(e, tile_offsets, flatten_ids, n_isects, b))
         return 1;
-    staged_pack(n, means2d, conics, colors4, opacities, nullptr, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, false,
+    staged_pack(n, means2d, conics, colors4, nullptr, opacities, nullptr, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, false,
                 e->stream);
     RasterIO io = make_io(e, ref_depth, nullptr, nullptr);
     io.deltaDepth = delta_depth;
@@ -731,7 +731,7 @@ extern "C" int gsb_gs_rasterize_ges_bwd(gsb_gs_t *e, int n, const float *means2d
     const int P = e->W * e->H;
     GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
     GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), e->stream));
-    staged_pack(n, means2d, conics, colors4, opacities, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, true,
+    staged_pack(n, means2d, conics, colors4, nullptr, opacities, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, true,
                 e->stream);
     pack_v_out(P, v_render4, v_alphas, e->v_out, e->v_depth, e->stream);
     staged_cut(P, ref_depth, delta_depth, e->cutImg, e->stream);
@@ -740,6 +740,104 @@ extern "C" int gsb_gs_rasterize_ges_bwd(gsb_gs_t *e, int n, const float *means2d
     raster_bwd(e->recs, e->bins, e->W, e->H, io, e->v_depth, e->grads, e->stream);
     staged_unpack_grads(n, e->recs, e->grads, v_means2d, v_conics, v_colors4, v_opacities, e->stream);
     GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream));
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- render_method "raw": depth-sorted bins, front-to-back compositing, and the fused SSIM map
+extern "C" int gsb_gs_isect_tiles_depth(gsb_gs_t *e, int n, const float *means2d, const int *radii, const float *depths, int *tiles_per_gauss,
+                                        int *n_isects)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means2d || !radii || !depths || !n_isects)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    GS_CUDA_OK(cudaMemsetAsync(e->bins.segCount, 0, sizeof(int) * (size_t)e->T * BIN_CHUNKS, e->stream));
+    staged_pack(n, means2d, nullptr, nullptr, depths, nullptr, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, tiles_per_gauss,
+                true, false, e->stream);
+    bin_tiles(e->recs, nullptr, n, e->bins, e->tileW, e->tileH, e->stream);
+    sort_tiles_depth(e->recs, e->bins, e->T, e->stream);
+    GS_CUDA_OK(cudaMemcpyAsync(e->hostInts, e->bins.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (e->hostInts[CNT_OVERFLOW] & 1)
+        return gs_set_error(__FILE__, __LINE__, "intersection capacity exceeded (gsb_gs_config.isect_capacity)");
+    *n_isects = e->hostInts[CNT_ISECTS];
+    return 0;
+}
+
+extern "C" int gsb_gs_isect_fetch_depth(gsb_gs_t *e, int n_isects, long long *isect_ids, int *flatten_ids, int *tile_offsets)
+{
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "null engine");
+    if (n_isects < 0 || n_isects > e->bins.isectCap)
+        return gs_set_error(__FILE__, __LINE__, "invalid n_isects");
+    if (isect_ids && n_isects)
+        isect_ids_depth(e->recs, e->bins, e->T, isect_ids, e->stream);
+    if (flatten_ids && n_isects)
+        GS_CUDA_OK(cudaMemcpyAsync(flatten_ids, e->bins.flattenSorted, sizeof(int) * (size_t)n_isects, cudaMemcpyDeviceToDevice, e->stream));
+    if (tile_offsets)
+        GS_CUDA_OK(cudaMemcpyAsync(tile_offsets, e->bins.tileOffsets, sizeof(int) * (size_t)e->T, cudaMemcpyDeviceToDevice, e->stream));
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_rasterize_fwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4, const float *opacities,
+                                    const float *background4, const int *tile_offsets, const int *flatten_ids, int n_isects, float *render4,
+                                    float *alphas, int *last_ids)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means2d || !conics || !colors4 || !opacities || !tile_offsets || (!flatten_ids && n_isects) || !render4 || !alphas || !last_ids)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    Bins b;
+    if (staged_bins(e, tile_offsets, flatten_ids, n_isects, b))
+        return 1;
+    staged_pack(n, means2d, conics, colors4, nullptr, opacities, nullptr, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false,
+                false, e->stream);
+    raw_fwd(e->recs, b, e->W, e->H, e->tileW, e->tileH, background4, render4, alphas, last_ids, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_rasterize_bwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4, const float *opacities,
+                                    const float *background4, const int *tile_offsets, const int *flatten_ids, int n_isects,
+                                    const float *render_alphas, const int *last_ids, const float *v_render4, const float *v_alphas,
+                                    float *v_means2d, float *v_conics, float *v_colors4, float *v_opacities)
+{
+    if (check_n(e, n))
+        return 1;
+    if (!means2d || !conics || !colors4 || !opacities || !tile_offsets || (!flatten_ids && n_isects) || !render_alphas || !last_ids ||
+        !v_render4 || !v_alphas || !v_means2d || !v_conics || !v_colors4 || !v_opacities)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    Bins b;
+    if (staged_bins(e, tile_offsets, flatten_ids, n_isects, b))
+        return 1;
+    staged_pack(n, means2d, conics, colors4, nullptr, opacities, nullptr, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false,
+                false, e->stream);
+    raw_bwd(n, e->recs, b, e->W, e->H, e->tileW, e->tileH, background4, render_alphas, last_ids, v_render4, v_alphas, e->grads, e->stream);
+    staged_unpack_grads(n, e->recs, e->grads, v_means2d, v_conics, v_colors4, v_opacities, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_ssim_fwd(gsb_gs_t *e, int planes, int height, int width, float C1, float C2, const float *img1, const float *img2,
+                               float *ssim_map, float *dm_dmu1, float *dm_dsigma1_sq, float *dm_dsigma12)
+{
+    if (!e || !img1 || !img2 || !ssim_map || planes <= 0 || height <= 0 || width <= 0)
+        return gs_set_error(__FILE__, __LINE__, "invalid argument");
+    if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr))
+        return gs_set_error(__FILE__, __LINE__, "the three derivative maps go together (train = true) or are all NULL");
+    ssim_fwd(planes, height, width, C1, C2, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_ssim_bwd(gsb_gs_t *e, int planes, int height, int width, const float *img1, const float *img2, const float *dL_dmap,
+                               const float *dm_dmu1, const float *dm_dsigma1_sq, const float *dm_dsigma12, float *dL_dimg1)
+{
+    if (!e || !img1 || !img2 || !dL_dmap || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1 || planes <= 0 || height <= 0 || width <= 0)
+        return gs_set_error(__FILE__, __LINE__, "invalid argument");
+    ssim_bwd(planes, height, width, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, dL_dimg1, e->stream);
     GS_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -129,8 +129,9 @@ __global__ void __launch_bounds__(128) k_staged_sh_bwd(int N, const float *__res
 
 // separate arrays -> packed 48-byte records (+ per-(tile, chunk) counts, tiles_per_gauss, backward work items)
 __global__ void __launch_bounds__(256) k_staged_pack(int N, const float *__restrict__ means2d, const float *__restrict__ conics,
-                                                      const float *__restrict__ colors4, const float *__restrict__ opac,
-                                                      const int *__restrict__ radii, SplatRec *recs, SplatGrad *grads, int *segCount,
+                                                      const float *__restrict__ colors4, const float *__restrict__ depths,
+                                                      const float *__restrict__ opac, const int *__restrict__ radii, SplatRec *recs,
+                                                      SplatGrad *grads, int *segCount,
                                                       int chunkSize, int tileW, int tileH, int W, int H, int *tilesPerGauss, int4 *items,
                                                       int itemCap, int *counters, int countTiles, int forBackward)
 {
@@ -157,6 +158,8 @@ __global__ void __launch_bounds__(256) k_staged_pack(int N, const float *__restr
         ca = conics[g * 3 + 0], cb = conics[g * 3 + 1], cc = conics[g * 3 + 2];
     if (colors4)
         r = colors4[g * 4 + 0], gr = colors4[g * 4 + 1], b = colors4[g * 4 + 2], d = colors4[g * 4 + 3];
+    if (depths)
+        d = depths[g];
     int bits = 7; // colours arrive already clamped; their gradient is returned unmasked (the caller's autograd applies clamp_min)
     if (countTiles)
     {
@@ -278,14 +281,14 @@ void staged_sh_bwd(int N, const float *dirs, const float *coeffs, const unsigned
     k_staged_sh_bwd<<<cdiv(N, 128), 128, 0, st>>>(N, dirs, coeffs, mask, v_colors, v_coeffs, v_dirs);
 }
 
-void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *opac, const int *radii, SplatRec *recs,
-                 SplatGrad *grads, const Bins &bins, int tileW, int tileH, int W, int H, int *tilesPerGauss, bool countTiles, bool forBackward,
-                 cudaStream_t st)
+void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *depths, const float *opac, const int *radii,
+                 SplatRec *recs, SplatGrad *grads, const Bins &bins, int tileW, int tileH, int W, int H, int *tilesPerGauss, bool countTiles,
+                 bool forBackward, cudaStream_t st)
 {
     if (N <= 0)
         return;
     GS_COUNT_LAUNCHES(1);
-    k_staged_pack<<<cdiv(N, 256), 256, 0, st>>>(N, means2d, conics, colors4, opac, radii, recs, grads, bins.segCount, bin_chunk_size(N), tileW,
+    k_staged_pack<<<cdiv(N, 256), 256, 0, st>>>(N, means2d, conics, colors4, depths, opac, radii, recs, grads, bins.segCount, bin_chunk_size(N), tileW,
                                                 tileH, W, H, tilesPerGauss, bins.items, bins.itemCap, bins.counters, countTiles ? 1 : 0,
                                                 forBackward ? 1 : 0);
 }

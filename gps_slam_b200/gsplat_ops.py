@@ -44,6 +44,12 @@ class GsplatOps:
         L.gsb_gs_rasterize_ges_fwd.argtypes = [p, i, p, p, p, p, p, f, p, p, i, p, p]
         L.gsb_gs_rasterize_ges_bwd.argtypes = [p, i, p, p, p, p, p, p, f, p, p, p, p, p, p]
         L.gsb_gs_adam_step.argtypes = [p, C.c_longlong, p, p, p, p, f, f, f, f, i]
+        L.gsb_gs_isect_tiles_depth.argtypes = [p, i, p, p, p, p, C.POINTER(C.c_int)]
+        L.gsb_gs_isect_fetch_depth.argtypes = [p, i, p, p, p]
+        L.gsb_gs_rasterize_fwd.argtypes = [p, i, p, p, p, p, p, p, p, i, p, p, p]
+        L.gsb_gs_rasterize_bwd.argtypes = [p, i, p, p, p, p, p, p, p, i, p, p, p, p, p, p, p, p]
+        L.gsb_gs_ssim_fwd.argtypes = [p, i, i, i, f, f, p, p, p, p, p, p]
+        L.gsb_gs_ssim_bwd.argtypes = [p, i, i, i, p, p, p, p, p, p, p]
 
     def close(self):
         self.eng.close()
@@ -123,3 +129,58 @@ class GsplatOps:
     # torch::optim::Adam::step on one tensor, in place
     def adam_step(self, param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-15):
         E._check(self.L.gsb_gs_adam_step(self.h, param.numel(), _p(param), _p(_f32(grad)), _p(exp_avg), _p(exp_avg_sq), lr, beta1, beta2, eps, step))
+
+    # ---- render_method "raw" + fused SSIM
+    # isectTiles + isectOffsetEncode (gsplat_wapper.cpp:14-50): bins ordered by (tile, depth)
+    def isect_tiles(self, means2d, radii, depths):
+        n = means2d.shape[-2]
+        tpg = torch.empty((1, n), dtype=torch.int32, device=self.dev)
+        cnt = C.c_int(0)
+        E._check(self.L.gsb_gs_isect_tiles_depth(self.h, n, _p(_f32(means2d)), _p(radii.contiguous()), _p(_f32(depths)), _p(tpg), C.byref(cnt)))
+        ni = cnt.value
+        isect_ids = torch.empty((ni,), dtype=torch.int64, device=self.dev)
+        flatten_ids = torch.empty((ni,), dtype=torch.int32, device=self.dev)
+        offsets = torch.empty((1, self.tile_h, self.tile_w), dtype=torch.int32, device=self.dev)
+        E._check(self.L.gsb_gs_isect_fetch_depth(self.h, ni, _p(isect_ids), _p(flatten_ids), _p(offsets)))
+        return tpg, isect_ids, flatten_ids, offsets
+
+    # gsplat::rasterize_to_pixels_fwd_tensor -> render_colors [1,H,W,4], render_alphas [1,H,W,1], last_ids [1,H,W]
+    def rasterize_to_pixels_fwd(self, means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids):
+        n = means2d.shape[-2]
+        render = torch.empty((1, self.H, self.W, 4), device=self.dev)
+        alphas = torch.empty((1, self.H, self.W, 1), device=self.dev)
+        last_ids = torch.empty((1, self.H, self.W), dtype=torch.int32, device=self.dev)
+        bg = _f32(backgrounds) if backgrounds is not None else None
+        E._check(self.L.gsb_gs_rasterize_fwd(self.h, n, _p(_f32(means2d)), _p(_f32(conics)), _p(_f32(colors)), _p(_f32(opacities)), _p(bg),
+                                             _p(isect_offsets.contiguous()), _p(flatten_ids.contiguous()), flatten_ids.numel(), _p(render),
+                                             _p(alphas), _p(last_ids)))
+        return render, alphas, last_ids
+
+    # gsplat::rasterize_to_pixels_bwd_tensor -> v_means2d, v_conics, v_colors, v_opacities
+    def rasterize_to_pixels_bwd(self, means2d, conics, colors, opacities, backgrounds, isect_offsets, flatten_ids, render_alphas, last_ids,
+                                v_render_colors, v_render_alphas):
+        n = means2d.shape[-2]
+        v_means2d, v_conics, v_colors = torch.empty_like(means2d), torch.empty_like(conics), torch.empty_like(colors)
+        v_opac = torch.empty_like(opacities)
+        bg = _f32(backgrounds) if backgrounds is not None else None
+        E._check(self.L.gsb_gs_rasterize_bwd(self.h, n, _p(_f32(means2d)), _p(_f32(conics)), _p(_f32(colors)), _p(_f32(opacities)), _p(bg),
+                                             _p(isect_offsets.contiguous()), _p(flatten_ids.contiguous()), flatten_ids.numel(),
+                                             _p(_f32(render_alphas)), _p(last_ids.contiguous()), _p(_f32(v_render_colors)),
+                                             _p(_f32(v_render_alphas)), _p(v_means2d), _p(v_conics), _p(v_colors), _p(v_opac)))
+        return v_means2d, v_conics, v_colors, v_opac
+
+    # fusedssim (ssim.cu:368-407): img [B,CH,H,W] -> ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12
+    def fusedssim(self, C1, C2, img1, img2, train=True):
+        B, CH, H, W = img1.shape
+        out = [torch.empty_like(img1) for _ in range(4 if train else 1)]
+        E._check(self.L.gsb_gs_ssim_fwd(self.h, B * CH, H, W, C1, C2, _p(_f32(img1)), _p(_f32(img2)), _p(out[0]),
+                                        _p(out[1]) if train else None, _p(out[2]) if train else None, _p(out[3]) if train else None))
+        return tuple(out)
+
+    # fusedssim_backward (ssim.cu:409-460) -> dL_dimg1
+    def fusedssim_backward(self, C1, C2, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12):
+        B, CH, H, W = img1.shape
+        d = torch.empty_like(img1)
+        E._check(self.L.gsb_gs_ssim_bwd(self.h, B * CH, H, W, _p(_f32(img1)), _p(_f32(img2)), _p(_f32(dL_dmap)), _p(_f32(dm_dmu1)),
+                                        _p(_f32(dm_dsigma1_sq)), _p(_f32(dm_dsigma12)), _p(d)))
+        return d

@@ -255,6 +255,32 @@ int gsb_gs_rasterize_ges_bwd(gsb_gs_t *e, int n, const float *means2d, const flo
 int gsb_gs_adam_step(gsb_gs_t *e, long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr, float beta1,
                      float beta2, float eps, int step);
 
+/* ---- render_method "raw" (RawGaussianModel::rawForward, src/raw_gs_model.cpp:37-186) and the fused SSIM term of computeLoss
+ * (src/raw_gs_model.cpp:383-395); same conventions as the staged entry points above.
+ *   gsb_gs_isect_tiles_depth  gsplat::isect_tiles_tensor + isect_offset_encode_tensor (rasterizer/isect_tiles.cu:132-430): bins ordered by
+ *                             (tile, camera depth); ties keep ascending Gaussian id like the reference's stable radix sort.
+ *                             gsb_gs_isect_fetch_depth: isect_ids int64 = tile << 32 | depth bits, flatten_ids, tile_offsets.
+ *   gsb_gs_rasterize_fwd      gsplat::rasterize_to_pixels_fwd_tensor (rasterize_to_pixels_fwd.cu:198-376), COLOR_DIM 4, optional
+ *                             background [4] (device): front-to-back alpha compositing -> render4 [H,W,4], alphas [H,W] (= 1 - T),
+ *                             last_ids [H,W] (bin index of the last splat that contributed).
+ *   gsb_gs_rasterize_bwd      gsplat::rasterize_to_pixels_bwd_tensor (rasterize_to_pixels_bwd.cu:289-511), absgrad = false.
+ *   gsb_gs_ssim_fwd / _bwd    fusedssim / fusedssim_backward (rasterizer/ssim.cu:368-460): planes = B * CH images of height x width,
+ *                             NCHW; the three derivative maps are NULL when train = false. */
+int gsb_gs_isect_tiles_depth(gsb_gs_t *e, int n, const float *means2d, const int *radii, const float *depths, int *tiles_per_gauss,
+                             int *n_isects);
+int gsb_gs_isect_fetch_depth(gsb_gs_t *e, int n_isects, long long *isect_ids, int *flatten_ids, int *tile_offsets);
+int gsb_gs_rasterize_fwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4, const float *opacities,
+                         const float *background4, const int *tile_offsets, const int *flatten_ids, int n_isects, float *render4,
+                         float *alphas, int *last_ids);
+int gsb_gs_rasterize_bwd(gsb_gs_t *e, int n, const float *means2d, const float *conics, const float *colors4, const float *opacities,
+                         const float *background4, const int *tile_offsets, const int *flatten_ids, int n_isects, const float *render_alphas,
+                         const int *last_ids, const float *v_render4, const float *v_alphas, float *v_means2d, float *v_conics,
+                         float *v_colors4, float *v_opacities);
+int gsb_gs_ssim_fwd(gsb_gs_t *e, int planes, int height, int width, float C1, float C2, const float *img1, const float *img2,
+                    float *ssim_map, float *dm_dmu1, float *dm_dsigma1_sq, float *dm_dsigma12);
+int gsb_gs_ssim_bwd(gsb_gs_t *e, int planes, int height, int width, const float *img1, const float *img2, const float *dL_dmap,
+                    const float *dm_dmu1, const float *dm_dsigma1_sq, const float *dm_dsigma12, float *dL_dimg1);
+
 /* state read-back for parity tests (synchronises) */
 enum
 {

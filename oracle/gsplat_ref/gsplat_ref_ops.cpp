@@ -68,6 +68,14 @@ TensorList rasterize_raw(Tensor means2d, Tensor conics, Tensor colors, Tensor op
                                     flatten_ids, absgrad);
 }
 
+TensorList rasterize_raw_bg(Tensor means2d, Tensor conics, Tensor colors, Tensor opacities, Tensor backgrounds, int64_t width, int64_t height,
+                            int64_t tile_size, Tensor isect_offsets, Tensor flatten_ids, bool absgrad)
+{
+    at::optional<Tensor> none, bg = backgrounds;
+    return RasterizeToPixels::apply(means2d, conics, colors, opacities, bg, none, (int)width, (int)height, (int)tile_size, isect_offsets,
+                                    flatten_ids, absgrad);
+}
+
 // the forward kernel alone (returns last_ids too): rasterize_to_pixels_fwd_ges.cu:338-407
 TensorList rasterize_ges_fwd(Tensor means2d, Tensor conics, Tensor colors, Tensor opacities, Tensor ref_depth_map, Tensor base_color_map,
                              int64_t width, int64_t height, int64_t tile_size, Tensor isect_offsets, Tensor flatten_ids, double delta_depth)
@@ -102,6 +110,7 @@ TORCH_LIBRARY(gsplat_ref, m)
     m.def("rasterize_ges", &rasterize_ges);
     m.def("rasterize_ges_fwd", &rasterize_ges_fwd);
     m.def("rasterize_raw", &rasterize_raw);
+    m.def("rasterize_raw_bg", &rasterize_raw_bg);
     m.def("fused_ssim_map", &fused_ssim_map);
     m.def("simple_knn", &simple_knn);
 }
