@@ -88,9 +88,9 @@ struct RasterIO
     float *alphas;          // RAW / RENDER
     float *rgb;             // RENDER
     float *depth;           // RENDER
-    float4 *v_out;          // TRAIN: (v_render_r, v_render_g, v_render_b, v_render_alpha)
+    float4 *v_out;          // [2 P]: per pixel (v_render_r, v_render_g, v_render_b, v_render_alpha | depth cut, -, -, -); the first half is
+                            // written in TRAIN mode, the depth-test threshold (clamped refDepth + deltaDepth) in RAW / TRAIN mode
     float *lossTile;        // TRAIN: per-tile sum |rgb - gt|
-    float *cut;             // RAW / TRAIN: per-pixel depth-test threshold (clamped refDepth + deltaDepth), read by the backward
 };
 
 #ifdef __CUDACC__
@@ -174,7 +174,7 @@ void staged_sh_bwd(int N, const float *dirs, const float *coeffs, const unsigned
 void staged_pack(int N, const float *means2d, const float *conics, const float *colors4, const float *depths, const float *opac, const int *radii,
                  SplatRec *recs, SplatGrad *grads, const Bins &bins, int tileW, int tileH, int W, int H, int *tilesPerGauss, bool countTiles,
                  bool forBackward, cudaStream_t st);
-void staged_cut(int P, const float *refDepth, float delta, float *cut, cudaStream_t st);
+void staged_cut(int P, const float *refDepth, float delta, float4 *v_out, cudaStream_t st);
 void staged_isect_ids(const Bins &bins, int T, long long *isectIds, cudaStream_t st);
 void staged_unpack_grads(int N, const SplatRec *recs, const SplatGrad *grads, float *v_means2d, float *v_conics, float *v_colors4, float *v_opac,
                          cudaStream_t st);

@@ -32,7 +32,6 @@ struct gsb_gs
     Bins bins;
     float4 *v_out;
     float *v_depth;
-    float *cutImg;
     float *lossTile;
     double *lossDev;
     int *scanTmp;
@@ -144,9 +143,8 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     rc |= dev_alloc(e, &e->bins.flattenSorted, (size_t)e->bins.isectCap);
     rc |= dev_alloc(e, &e->bins.items, (size_t)e->bins.itemCap);
     rc |= dev_alloc(e, &e->bins.counters, (size_t)CNT_TOTAL);
-    rc |= dev_alloc(e, &e->v_out, P);
+    rc |= dev_alloc(e, &e->v_out, 2 * P);
     rc |= dev_alloc(e, &e->v_depth, P);
-    rc |= dev_alloc(e, &e->cutImg, P);
     rc |= dev_alloc(e, &e->lossTile, (size_t)e->T);
     rc |= dev_alloc(e, &e->lossDev, 1);
     rc |= dev_alloc(e, &e->scanTmp, (size_t)e->cap / 1024 + 2);
@@ -333,7 +331,7 @@ static RasterIO make_io(const gsb_gs *e, const float *ref_depth, const float *ba
     io.refDepth = ref_depth, io.baseColor = base_color, io.gt = gt;
     io.deltaDepth = e->cfg.delta_depth;
     io.clampRef = 1;
-    io.v_out = e->v_out, io.lossTile = e->lossTile, io.cut = e->cutImg;
+    io.v_out = e->v_out, io.lossTile = e->lossTile;
     return io;
 }
 
@@ -438,7 +436,7 @@ extern "C" int gsb_gs_read(gsb_gs_t *e, int what, void *dst, size_t bytes)
     case GSB_GS_SPLAT_GRADS: src = e->grads, avail = (size_t)e->cap * sizeof(SplatGrad); break;
     case GSB_GS_TILE_OFFSETS: src = e->bins.tileOffsets, avail = (size_t)(e->T + 1) * 4; break;
     case GSB_GS_FLATTEN_IDS: src = e->bins.flattenSorted, avail = (size_t)e->bins.isectCap * 4; break;
-    case GSB_GS_V_OUT: src = e->v_out, avail = P * 16; break;
+    case GSB_GS_V_OUT: src = e->v_out, avail = P * 32; break;
     case GSB_GS_COUNTERS: src = e->bins.counters, avail = CNT_TOTAL * 4; break;
     case GSB_GS_GRAD_MEANS: src = e->dbg.means, avail = (size_t)e->cap * 12; break;
     case GSB_GS_GRAD_SCALES: src = e->dbg.scales, avail = (size_t)e->cap * 12; break;
@@ -734,7 +732,7 @@ extern "C" int gsb_gs_rasterize_ges_bwd(gsb_gs_t *e, int n, const float *means2d
     staged_pack(n, means2d, conics, colors4, nullptr, opacities, radii, e->recs, e->grads, e->bins, e->tileW, e->tileH, e->W, e->H, nullptr, false, true,
                 e->stream);
     pack_v_out(P, v_render4, v_alphas, e->v_out, e->v_depth, e->stream);
-    staged_cut(P, ref_depth, delta_depth, e->cutImg, e->stream);
+    staged_cut(P, ref_depth, delta_depth, e->v_out, e->stream);
     RasterIO io = make_io(e, ref_depth, nullptr, nullptr);
     io.deltaDepth = delta_depth, io.clampRef = 0;
     raster_bwd(e->recs, e->bins, e->W, e->H, io, e->v_depth, e->grads, e->stream);

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256, 6) k_raster_fwd(const SplatRec *__restric
     float rd = (io.clampRef && rdRaw < 0.01f) ? 1000.0f : rdRaw;
     const float cut = rd + io.deltaDepth;
     if (MODE != RASTER_RENDER && inside)
-        io.cut[pix] = cut; // depth-test threshold per pixel, read back by the rasteriser backward
+        io.v_out[2 * pix + 1] = make_float4(cut, 0.f, 0.f, 0.f); // depth-test threshold per pixel, read back by the rasteriser backward
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, w = 0.f;
 
     for (int b = start; b < end; b += RB)
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256, 6) k_raster_fwd(const SplatRec *__restric
         float v1 = d1 > 0.f ? invCount : (d1 < 0.f ? -invCount : 0.f);
         float v2 = d2 > 0.f ? invCount : (d2 < 0.f ? -invCount : 0.f);
         float va = -(v0 * r0 + v1 * r1 + v2 * r2) / w1;
-        io.v_out[pix] = make_float4(v0 / w1, v1 / w1, v2 / w1, va);
+        io.v_out[2 * pix] = make_float4(v0 / w1, v1 / w1, v2 / w1, va);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
@@ -254,8 +254,8 @@ __device__ __forceinline__ float halfwarp_reduce16(float (&v)[16], int lane)
 // rectangles.  HAS_VD: a depth-channel gradient image is supplied (depth_weight > 0; off in every release config).
 template <bool HAS_VD>
 __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restrict__ recs, const int4 *__restrict__ items, int *counters, int itemCap,
-                                                        int W, const float *__restrict__ cutImg, const float4 *__restrict__ v_out,
-                                                        const float *__restrict__ v_depthImg, SplatGrad *__restrict__ grads)
+                                                        int W, const float4 *__restrict__ v_out, const float *__restrict__ v_depthImg,
+                                                        SplatGrad *__restrict__ grads)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
@@ -327,57 +327,50 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
         // gradient sums; the conic / mean gradients are accumulated as moments of t = v_sigma over (dx, dy):
         // v_conic = (Sxx/2, Sxy, Syy/2), v_mean2d = (a Sx + b Sy, b Sx + c Sy)
         float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f, vo = 0.f;
-        // Software pipeline: the image reads of step k+1 (depth cut + dL/d render, 20 B per pixel, L2 / L1 resident) are issued before
-        // the arithmetic of step k, unconditionally for every pixel of the rectangle, so that their latency is covered by a full step.
+        // Per-pixel record of the backward: 32 bytes = (dL/d render rgb, dL/d alpha | depth cut, -, -, -), written by the forward, so one
+        // address serves both reads.  Software pipeline, unrolled by two so that the in-flight buffers alternate without register
+        // copies: the reads of step k+1 are issued, unconditionally for every pixel of the rectangle, before the arithmetic of step k.
         int id0 = p0 + hl;
-        float cutN[2], vdpN[2];
-        float4 voN[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++)
+        struct PixData
         {
-            cutN[u] = -1e30f, vdpN[u] = 0.f, voN[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (id0 + u * 16 < p1)
-            {
-                cutN[u] = __ldg(&cutImg[pix[u]]);
-                voN[u] = __ldg(&v_out[pix[u]]);
-                if (HAS_VD)
-                    vdpN[u] = __ldg(&v_depthImg[pix[u]]);
-            }
-        }
-        for (int k = 0; k < steps; k++, id0 += 32)
+            float4 vo[2];
+            float cut[2], vdp[2], dx[2], dy[2];
+        };
+        auto fetch = [&](PixData &d, int idBase)
         {
-            float dxs[2], dys[2], cuts[2], vdps[2];
-            float4 vos[2];
 #pragma unroll
             for (int u = 0; u < 2; u++)
             {
-                dxs[u] = q0.x - px[u], dys[u] = q0.y - py[u];
-                cuts[u] = cutN[u], vdps[u] = vdpN[u], vos[u] = voN[u];
-                // advance to the pixel 32 ids further and start its reads
+                d.dx[u] = q0.x - px[u], d.dy[u] = q0.y - py[u];
+                d.cut[u] = -1e30f, d.vdp[u] = 0.f, d.vo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idBase + u * 16 < p1)
+                {
+                    const float4 *rec = v_out + 2 * (size_t)pix[u];
+                    d.vo[u] = __ldg(rec);
+                    d.cut[u] = __ldg(reinterpret_cast<const float *>(rec + 1));
+                    if (HAS_VD)
+                        d.vdp[u] = __ldg(&v_depthImg[pix[u]]);
+                }
+                // advance to the pixel 32 ids further
                 px[u] += r32f, py[u] += q32f, pix[u] += dpix;
                 if (px[u] > xEnd)
                     px[u] -= rwf, py[u] += 1.0f, pix[u] += dwrap;
-                cutN[u] = -1e30f;
-                if (id0 + 32 + u * 16 < p1)
-                {
-                    cutN[u] = __ldg(&cutImg[pix[u]]);
-                    voN[u] = __ldg(&v_out[pix[u]]);
-                    if (HAS_VD)
-                        vdpN[u] = __ldg(&v_depthImg[pix[u]]);
-                }
             }
+        };
+        auto consume = [&](const PixData &d)
+        {
 #pragma unroll
             for (int u = 0; u < 2; u++)
             {
-                const float dx = dxs[u], dy = dys[u], vdp = vdps[u];
+                const float dx = d.dx[u], dy = d.dy[u], vdp = d.vdp[u];
                 const float s2 = fmaf(dx, fmaf(B, dy, A * dx), (C * dy) * dy);
                 const float vis = ex2_approx(-s2);
                 const float ar = opac * vis;
                 const float alpha = fminf(0.999f, ar);
                 // (pixels beyond the item carry cut = -1e30 and fail the depth test)
-                if (s2 < 0.f || alpha < 1.f / 255.f || q1.w > cuts[u])
+                if (s2 < 0.f || alpha < 1.f / 255.f || q1.w > d.cut[u])
                     continue;
-                const float4 vo4 = vos[u];
+                const float4 vo4 = d.vo[u];
                 vr += alpha * vo4.x;
                 vg += alpha * vo4.y;
                 vb += alpha * vo4.z;
@@ -400,6 +393,15 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
                     vo += qv;
                 }
             }
+        };
+        PixData dA, dB;
+        fetch(dA, id0);
+        for (int k = 0; k < steps; k += 2, id0 += 64)
+        {
+            fetch(dB, id0 + 32);
+            consume(dA);
+            fetch(dA, id0 + 64);
+            consume(dB); // (a step beyond `steps` only sees pixels beyond the item: nothing passes)
         }
         // slots follow the float layout of SplatGrad: (vx, vy, vo, vd | vca, vcb, vcc, - | vr, vg, vb, -)
         float v16[16];
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(256) k_composite(const float *__restrict__ acc
     float lsum = 0.f;
     if (inside)
     {
-        io.cut[pix] = ((io.clampRef && rdRaw < 0.01f) ? 1000.0f : rdRaw) + io.deltaDepth;
+        io.v_out[2 * pix + 1] = make_float4(((io.clampRef && rdRaw < 0.01f) ? 1000.0f : rdRaw) + io.deltaDepth, 0.f, 0.f, 0.f);
         const float *gt = io.gt + (size_t)pix * 3;
         float d0 = r0 - __ldg(gt + 0), d1 = r1 - __ldg(gt + 1), d2 = r2 - __ldg(gt + 2);
         lsum = fabsf(d0) + fabsf(d1) + fabsf(d2);
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(256) k_composite(const float *__restrict__ acc
         float v1 = d1 > 0.f ? invCount : (d1 < 0.f ? -invCount : 0.f);
         float v2 = d2 > 0.f ? invCount : (d2 < 0.f ? -invCount : 0.f);
         float va = -(v0 * r0 + v1 * r1 + v2 * r2) / w1;
-        io.v_out[pix] = make_float4(v0 / w1, v1 / w1, v2 / w1, va);
+        io.v_out[2 * pix] = make_float4(v0 / w1, v1 / w1, v2 / w1, va);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
@@ -496,7 +498,7 @@ __global__ void k_pack_v_out(int P, const float *__restrict__ v_render4, const f
     if (i >= P)
         return;
     float4 r = reinterpret_cast<const float4 *>(v_render4)[i];
-    v_out[i] = make_float4(r.x, r.y, r.z, v_alphas[i]);
+    v_out[2 * i] = make_float4(r.x, r.y, r.z, v_alphas[i]);
     v_depth[i] = r.w;
 }
 
@@ -540,9 +542,9 @@ void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const Rast
     }
     const int grid = sms * ctasPerSm[v] * BWD_GRID_MULT;
     if (v_depth)
-        k_raster_bwd<true><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, v_depth, grads);
+        k_raster_bwd<true><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.v_out, v_depth, grads);
     else
-        k_raster_bwd<false><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.cut, io.v_out, nullptr, grads);
+        k_raster_bwd<false><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.v_out, nullptr, grads);
 }
 
 void composite(int mode, const float *acc5, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st)

@@ -226,11 +226,11 @@ __global__ void __launch_bounds__(256) k_staged_unpack_grads(int N, const SplatR
     v_colors4[g * 4 + 0] = g2.x, v_colors4[g * 4 + 1] = g2.y, v_colors4[g * 4 + 2] = g2.z, v_colors4[g * 4 + 3] = g0.w;
 }
 
-__global__ void __launch_bounds__(256) k_staged_cut(int P, const float *__restrict__ refDepth, float delta, float *cut)
+__global__ void __launch_bounds__(256) k_staged_cut(int P, const float *__restrict__ refDepth, float delta, float4 *v_out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P)
-        cut[i] = refDepth[i] + delta;
+        v_out[2 * i + 1] = make_float4(refDepth[i] + delta, 0.f, 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(256) k_staged_adam(int n, float *p, const float *__restrict__ g, float *m, float *v, AdamScalars a, float stepSize)
@@ -308,10 +308,10 @@ void staged_unpack_grads(int N, const SplatRec *recs, const SplatGrad *grads, fl
     k_staged_unpack_grads<<<cdiv(N, 256), 256, 0, st>>>(N, recs, grads, v_means2d, v_conics, v_colors4, v_opac);
 }
 
-void staged_cut(int P, const float *refDepth, float delta, float *cut, cudaStream_t st)
+void staged_cut(int P, const float *refDepth, float delta, float4 *v_out, cudaStream_t st)
 {
     GS_COUNT_LAUNCHES(1);
-    k_staged_cut<<<cdiv(P, 256), 256, 0, st>>>(P, refDepth, delta, cut);
+    k_staged_cut<<<cdiv(P, 256), 256, 0, st>>>(P, refDepth, delta, v_out);
 }
 
 void staged_adam(int n, float *p, const float *g, float *m, float *v, const AdamScalars &a, float step_size, cudaStream_t st)

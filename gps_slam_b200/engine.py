@@ -474,7 +474,8 @@ class GaussianEngine:
         return off, ids
 
     def v_out(self):
-        return self.read(GS_V_OUT, np.float32, (self.H, self.W, 4))
+        """dL/d render (rgb, alpha) per pixel; the engine stores 8 floats per pixel (gradient | depth cut, padding)"""
+        return np.ascontiguousarray(self.read(GS_V_OUT, np.float32, (self.H, self.W, 8))[..., :4])
 
     def param_grads(self, n):
         ids = dict(means=GS_GRAD_MEANS, scales=GS_GRAD_SCALES, quats=GS_GRAD_QUATS, featuresDc=GS_GRAD_DC, featuresRest=GS_GRAD_REST,

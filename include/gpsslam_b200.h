@@ -288,7 +288,7 @@ enum
     GSB_GS_SPLAT_GRADS = 1,     /* [N] 12 floats: v_mean2d.xy, v_opacity, v_depth | v_conic abc, 0 | v_rgb, 0            */
     GSB_GS_TILE_OFFSETS = 2,    /* int[T+1]  (isect_offsets + n_isects)                                                  */
     GSB_GS_FLATTEN_IDS = 3,     /* int[n_isects]                                                                         */
-    GSB_GS_V_OUT = 4,           /* float4[H*W]: dL/d render rgb, dL/d alpha                                              */
+    GSB_GS_V_OUT = 4,           /* 8 floats per pixel [H*W]: dL/d render rgb, dL/d alpha | depth cut, 3 x padding        */
     GSB_GS_COUNTERS = 5,        /* int[8]: n_isects, n_items, overflow bits, -, n_visible, ...                           */
     GSB_GS_GRAD_MEANS = 6, GSB_GS_GRAD_SCALES = 7, GSB_GS_GRAD_QUATS = 8, GSB_GS_GRAD_DC = 9, GSB_GS_GRAD_REST = 10, GSB_GS_GRAD_OPAC = 11
 };
