@@ -48,7 +48,7 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
@@ -69,31 +69,42 @@ class ClockSampler:
         for line in self.p.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1: time.time() bounds of the timed region; the sampler itself is started before the warm-up steps (nvidia-smi needs
+        ~0.2 s to deliver its first line, longer than a timed region of a few steps) and only the samples inside [t0, t1] are kept"""
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        inside = [r for r in rows if t0 is None or (t0 - 0.02 <= r[0] <= t1 + 0.02)]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (no sample fell inside the timed region)"
+        sm, mx, reasons = [], [], set()
+        for _, a, b, fl in inside:
+            sm.append(a)
+            mx.append(b)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), fl):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def ncu_traffic():
@@ -256,6 +267,8 @@ def main():
         """W warm-up + K timed steps from a fresh map; returns (ms, launches, stats)"""
         pipe.reset()
         f = 0
+        sampler = ClockSampler(local)
+        sampler.start()
         with torch.cuda.stream(stream):
             for _ in range(args.warmup):
                 for _ in range(FRAMES_PER_STEP):
@@ -263,8 +276,7 @@ def main():
                     f += 1
                 pipe.end_of_step(resident)
             barrier()
-            sampler = ClockSampler(local)
-            sampler.start()
+            t_begin = time.time()
             l0 = E.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -275,9 +287,10 @@ def main():
                 pipe.end_of_step(resident)
             e1.record(stream)
             barrier()
+            t_end = time.time()
             ms = e0.elapsed_time(e1)
             launches = E.launch_count() - l0
-            clocks = sampler.stop()
+            clocks = sampler.stop(t_begin, t_end)
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
