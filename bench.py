@@ -327,7 +327,8 @@ def main():
             "metric": "slam_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": pipe.scaling(), "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": slam.workload_name(mode) + ("" if args.track == 0 else ", online ICP tracking (use_gt_pose=false)"),
+            "config": dict({"workload": slam.workload_name(mode) if args.track == 0 else slam.workload_name(mode).replace(
+                                "use_gt_pose=true", "use_gt_pose=false: online ICP tracking, %s tracker" % ("extended" if args.track == 1 else "icp")),
                             "parallelism": "single GPU" if world == 1 else "Gaussians sharded by spatial block over %d GPUs, one [H,W,5] "
                                            "all-reduce per optimiser iteration; TSDF replicated" % world, "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
                             "l2": "no explicit flush: every frame is new input (4.9 MB) and each step streams the visible voxel "
