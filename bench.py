@@ -280,15 +280,19 @@ def main():
             l0 = E.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
+            marks = [e0]
             for _ in range(args.steps):
                 for _ in range(FRAMES_PER_STEP):
                     pipe.process_frame(f, rgba if resident else rgba_h, depth if resident else depth_h, poses, resident)
                     f += 1
                 pipe.end_of_step(resident)
-            e1.record(stream)
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record(stream)
+            e1 = marks[-1]
             barrier()
             t_end = time.time()
             ms = e0.elapsed_time(e1)
+            run_leg.per_step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(len(marks) - 1)]
             launches = E.launch_count() - l0
             clocks = sampler.stop(t_begin, t_end)
         if world > 1:
@@ -298,6 +302,7 @@ def main():
         return ms, launches, clocks
 
     ms, launches, clocks = run_leg(True)
+    per_step_ms = list(run_leg.per_step_ms)
     stats = pipe.stats()
     psnr = eval_psnr(pipe, intr, poses, rgba, n_frames, dev) if mode == "train" else None
     ms_e2e = run_leg(False)[0] if not args.no_e2e else float("nan")
@@ -332,7 +337,7 @@ def main():
                             "parallelism": "single GPU" if world == 1 else "Gaussians sharded by spatial block over %d GPUs, one [H,W,5] "
                                            "all-reduce per optimiser iteration; TSDF replicated" % world, "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
                             "l2": "no explicit flush: every frame is new input (4.9 MB) and each step streams the visible voxel "
-                                  "blocks 10x (V x 8 KB per frame), working set > 126 MB L2", "quality": psnr}, **stats),
+                                  "blocks 10x (V x 8 KB per frame), working set > 126 MB L2", "quality": psnr, "ms_per_step_each": per_step_ms}, **stats),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roofline, "cpu_baseline": cpu,

@@ -146,7 +146,6 @@ constexpr int TILE = 16;
 constexpr int BIN_CHUNKS = 64; // id-range chunks of the counting sort by (tile, chunk)
 inline int bin_chunk_size(int nUpper) { return nUpper > BIN_CHUNKS ? (nUpper + BIN_CHUNKS - 1) / BIN_CHUNKS : 1; }
 constexpr int BWD_PIXELS_PER_ITEM = 2048;
-constexpr int BWD_GROUPS_PER_ITEM = 64;
 constexpr int PARAMS_PER_GAUSSIAN = 59;
 
 // ---- gs_project.cu

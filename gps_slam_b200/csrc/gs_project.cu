@@ -38,12 +38,6 @@ __device__ __forceinline__ void tile_rect(float m2x, float m2y, int radius, int 
     y1 = (int)min((unsigned)ceilf(ty + tr), (unsigned)tileH);
 }
 
-__device__ __forceinline__ int bwd_groups(int radius)
-{
-    float r = (float)radius;
-    return (int)((4.0f * r * r + 32.0f - 1.0f) / 32.0f); // groups_per_gauss, evaluated in float like the reference (:87)
-}
-
 __device__ __forceinline__ void load_coeffs(const ParamPtrs &p, int g, float *cl /* [16][3] */)
 {
     cl[0] = p.dc[g * 3 + 0], cl[1] = p.dc[g * 3 + 1], cl[2] = p.dc[g * 3 + 2];

@@ -26,12 +26,6 @@ __device__ __forceinline__ float ex2_approx(float x)
     return y;
 }
 
-#ifndef BWD_PREFETCH_CURSOR
-#define BWD_PREFETCH_CURSOR 0
-#endif
-#ifndef BWD_GRID_MULT
-#define BWD_GRID_MULT 1
-#endif
 constexpr int RB = 256; // splats per staged batch = threads per tile CTA
 
 template <int MODE>
@@ -188,36 +182,6 @@ __global__ void __launch_bounds__(256, 6) k_raster_fwd(const SplatRec *__restric
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Sum 16 per-lane values over the warp with 16 shuffles (instead of 16 x 5): at each halving step a lane keeps one half of its
-// values and hands the other half to its partner.  Returns, in lane l, the warp total of slot l >> 1 (each total is held twice).
-__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane)
-{
-    const unsigned full = 0xffffffffu;
-    float w8[8], w4[4], w2[2];
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-    {
-        float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(full, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-    {
-        float send = h8 ? w8[i] : w8[i + 4], keep = h8 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(full, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-    {
-        float send = h4 ? w4[i] : w4[i + 2], keep = h4 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(full, send, 4);
-    }
-    float send = h2 ? w2[0] : w2[1], keep = h2 ? w2[1] : w2[0];
-    float w1 = keep + __shfl_xor_sync(full, send, 2);
-    return w1 + __shfl_xor_sync(full, w1, 1);
-}
-
 // Sum 16 per-lane values over each HALF warp (lanes 0-15 and 16-31 independently) with 15 shuffles: at each halving step a lane
 // keeps one half of its values and hands the other half to its partner.  Returns, in lane l, the half-warp total of slot l & 15.
 __device__ __forceinline__ float halfwarp_reduce16(float (&v)[16], int lane)
@@ -264,30 +228,17 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
     int *cursor = counters + CNT_BWD_CURSOR;
     constexpr int GRAB = 8; // consecutive items per cursor bump (same-address atomics are the scarce resource)
     int it = 0, itEnd = 0;
-    // the cursor bump for the NEXT batch is issued when a batch starts, so that its round trip to L2 is hidden behind the batch
-    int nextBatch = 0;
-#if BWD_PREFETCH_CURSOR
-    if (lane == 0)
-        nextBatch = atomicAdd(cursor, GRAB);
-#endif
     for (;;)
     {
         if (it >= itEnd)
         {
-#if BWD_PREFETCH_CURSOR
-            it = __shfl_sync(full, nextBatch, 0);
-#else
+            // (prefetching the next batch's cursor bump while a batch runs was measured 12 % slower: it coarsens the distribution)
             if (lane == 0)
-                nextBatch = atomicAdd(cursor, GRAB);
-            it = __shfl_sync(full, nextBatch, 0);
-#endif
+                it = atomicAdd(cursor, GRAB);
+            it = __shfl_sync(full, it, 0);
             if (it >= nItems)
                 break;
             itEnd = min(it + GRAB, nItems);
-#if BWD_PREFETCH_CURSOR
-            if (lane == 0)
-                nextBatch = atomicAdd(cursor, GRAB);
-#endif
         }
         const int mine = it + half;
         const bool live = mine < itEnd;
@@ -540,7 +491,7 @@ void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const Rast
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
             sms = 148;
     }
-    const int grid = sms * ctasPerSm[v] * BWD_GRID_MULT;
+    const int grid = sms * ctasPerSm[v];
     if (v_depth)
         k_raster_bwd<true><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.v_out, v_depth, grads);
     else
