@@ -1,0 +1,102 @@
+"""Checkpoint / wire formats of the reference, on the host:
+
+  * Gaussians: the 3DGS point_cloud.ply written by RawGaussianParams::savePly (reference src/raw_gs_param.cpp:159-218): binary little
+    endian, per vertex x y z, nx ny nz (zeros), f_dc_0..2, f_rest_0..44 (featuresRest TRANSPOSED to [3,15] then flattened),
+    opacity (logit), scale_0..2 (log), rot_0..3 (w x y z).
+  * TSDF scene: the Scene/ directory of ITMBasicEngine::SaveToFile (reference InfiniTAM/ITMLib/Core/ITMBasicEngine.tpp:119-135;
+    Objects/Scene/ITMVoxelBlockHash.h:129-155, ITMLocalVBA.h:36-66; ORUtils/MemoryBlockPersister.h:188-207): every *.dat file is a
+    size_t element count followed by the raw array -- hash.dat (ITMHashEntry[1179648]), excess.dat (int[131072]), voxel.dat
+    (ITMVoxel_s_rgb[blocks*512]), alloc.dat (int[blocks]); last.txt holds lastFreeExcessListId, vba.txt "lastFreeBlockId allocatedSize".
+    The engine never returns blocks to the free lists (no swapping, as in the SLAM configuration), so both lists stay the identity
+    permutation the reference initialises them with, and the files are byte-identical to the reference's (tests/test_checkpoint_gpu.py).
+
+Pure numpy; the device side is gsb_tsdf_read / gsb_tsdf_counter / gsb_tsdf_load_scene and gsb_gs_get_params / gsb_gs_set_params."""
+import os
+
+import numpy as np
+
+from . import engine as E
+
+PLY_PROPS = (["x", "y", "z", "nx", "ny", "nz"] + ["f_dc_%d" % i for i in range(3)] + ["f_rest_%d" % i for i in range(45)] + ["opacity"] +
+             ["scale_%d" % i for i in range(3)] + ["rot_%d" % i for i in range(4)])
+
+
+def save_ply(path, params):
+    """params: dict of the six parameter arrays (means [N,3], scales log [N,3], quats wxyz [N,4], featuresDc [N,3], featuresRest [N,15,3],
+    opacities logit [N,1]) as GaussianEngine.get_params() returns them"""
+    n = params["means"].shape[0]
+    rest = np.asarray(params["featuresRest"], np.float32).reshape(n, 15, 3).transpose(0, 2, 1).reshape(n, 45)
+    rows = np.concatenate([np.asarray(params["means"], np.float32).reshape(n, 3), np.zeros((n, 3), np.float32),
+                           np.asarray(params["featuresDc"], np.float32).reshape(n, 3), rest,
+                           np.asarray(params["opacities"], np.float32).reshape(n, 1), np.asarray(params["scales"], np.float32).reshape(n, 3),
+                           np.asarray(params["quats"], np.float32).reshape(n, 4)], 1).astype("<f4")
+    with open(path, "wb") as f:
+        f.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % n).encode())
+        for p in PLY_PROPS:
+            f.write(("property float %s\n" % p).encode())
+        f.write(b"end_header\n")
+        f.write(rows.tobytes())
+
+
+def load_ply(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    end = data.index(b"end_header\n") + len(b"end_header\n")
+    header = data[:end].decode().split("\n")
+    if header[0] != "ply" or "binary_little_endian" not in header[1]:
+        raise ValueError("%s is not a binary little-endian ply" % path)
+    n = int([h for h in header if h.startswith("element vertex")][0].split()[2])
+    props = [h.split()[2] for h in header if h.startswith("property float")]
+    if props != PLY_PROPS:
+        raise ValueError("%s does not have the reference's 3DGS property list" % path)
+    rows = np.frombuffer(data, "<f4", n * len(props), end).reshape(n, len(props))
+    return dict(means=rows[:, 0:3].copy(), featuresDc=rows[:, 6:9].copy(),
+                featuresRest=rows[:, 9:54].reshape(n, 3, 15).transpose(0, 2, 1).copy(), opacities=rows[:, 54:55].copy(),
+                scales=rows[:, 55:58].copy(), quats=rows[:, 58:62].copy())
+
+
+def _write_block(path, arr):
+    with open(path, "wb") as f:
+        f.write(np.uint64(arr.size).tobytes())
+        f.write(np.ascontiguousarray(arr).tobytes())
+
+
+def _read_block(path, dtype):
+    with open(path, "rb") as f:
+        n = int(np.frombuffer(f.read(8), np.uint64)[0])
+        a = np.frombuffer(f.read(), dtype)
+    if a.size != n:
+        raise ValueError("%s: header says %d elements, file holds %d" % (path, n, a.size))
+    return a
+
+
+def save_scene(directory, tsdf):
+    """ITMBasicEngine::SaveToFile for a TsdfEngine: writes <directory>/Scene/*"""
+    scene = os.path.join(directory, "Scene")
+    os.makedirs(scene, exist_ok=True)
+    os.makedirs(os.path.join(directory, "Relocaliser"), exist_ok=True)
+    last_block, last_excess = tsdf.counter(0), tsdf.counter(1)
+    _write_block(os.path.join(scene, "voxel.dat"), tsdf.voxels().reshape(-1))
+    _write_block(os.path.join(scene, "alloc.dat"), np.arange(tsdf.num_blocks, dtype=np.int32))
+    with open(os.path.join(scene, "vba.txt"), "w") as f:
+        f.write("%d %d" % (last_block, tsdf.num_blocks * 512))
+    with open(os.path.join(scene, "last.txt"), "w") as f:
+        f.write("%d" % last_excess)
+    _write_block(os.path.join(scene, "hash.dat"), tsdf.hash_entries())
+    _write_block(os.path.join(scene, "excess.dat"), np.arange(0x20000, dtype=np.int32))
+
+
+def load_scene(directory, tsdf):
+    """ITMBasicEngine::LoadFromFile for a TsdfEngine"""
+    scene = os.path.join(directory, "Scene")
+    hash_entries = _read_block(os.path.join(scene, "hash.dat"), E.HASH_ENTRY)
+    voxels = _read_block(os.path.join(scene, "voxel.dat"), E.VOXEL)
+    alloc = _read_block(os.path.join(scene, "alloc.dat"), np.int32)
+    excess = _read_block(os.path.join(scene, "excess.dat"), np.int32)
+    if not (np.array_equal(alloc, np.arange(alloc.size)) and np.array_equal(excess, np.arange(excess.size))):
+        raise E.EngineError("free lists are not the identity permutation (scene saved by an engine with swapping): not supported")
+    with open(os.path.join(scene, "vba.txt")) as f:
+        last_block = int(f.read().split()[0])
+    with open(os.path.join(scene, "last.txt")) as f:
+        last_excess = int(f.read().split()[0])
+    tsdf.load_scene(hash_entries, voxels, last_block, last_excess)

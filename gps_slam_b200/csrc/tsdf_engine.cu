@@ -176,6 +176,29 @@ extern "C" int gsb_tsdf_reset(gsb_tsdf_t *e)
     return 0;
 }
 
+// ITMBasicEngine::LoadFromFile (Core/ITMBasicEngine.tpp:137-171) without the file I/O: resetAll(), then the scene arrays of
+// ITMScene::LoadFromDirectory (hash.dat, voxel.dat, last.txt, vba.txt; Objects/Scene/ITMVoxelBlockHash.h:143-155, ITMLocalVBA.h:52-66)
+// are taken from host memory.  Like the reference, visibility is rebuilt by the next frame.
+extern "C" int gsb_tsdf_load_scene(gsb_tsdf_t *e, const void *hash_entries_host, size_t n_entries, const void *voxels_host, size_t n_voxels,
+                                   int last_free_block_id, int last_free_excess_list_id)
+{
+    if (!e || !hash_entries_host || !voxels_host)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    if (n_entries != (size_t)e->scene.E || n_voxels != (size_t)e->scene.numBlocks * SDF_BLOCK_SIZE3)
+        return gs_set_error(__FILE__, __LINE__, "scene arrays do not match this engine's hash table / voxel block array sizes");
+    if (last_free_block_id < -1 || last_free_block_id >= e->scene.numBlocks || last_free_excess_list_id < -1 ||
+        last_free_excess_list_id >= SDF_EXCESS_LIST_SIZE)
+        return gs_set_error(__FILE__, __LINE__, "free-list heads out of range");
+    if (gsb_tsdf_reset(e))
+        return 1;
+    E_CUDA(cudaMemcpyAsync(e->scene.table, hash_entries_host, n_entries * sizeof(HashEntry), cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(cudaMemcpyAsync(e->scene.vba, voxels_host, n_voxels * sizeof(Voxel), cudaMemcpyHostToDevice, e->stream));
+    const int heads[2] = {last_free_block_id, last_free_excess_list_id};
+    E_CUDA(cudaMemcpyAsync(e->scene.state, heads, sizeof heads, cudaMemcpyHostToDevice, e->stream));
+    E_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 extern "C" int gsb_tsdf_set_stream(gsb_tsdf_t *e, void *st)
 {
     e->stream = st ? (cudaStream_t)st : e->ownStream;

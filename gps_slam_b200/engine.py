@@ -245,6 +245,13 @@ class TsdfEngine:
         a = np.ascontiguousarray(invM16, dtype=np.float32)
         _check(self.L.gsb_tsdf_set_pose(self.h_, _ptr(a)))
 
+    def load_scene(self, hash_entries, voxels, last_free_block, last_free_excess):
+        """ITMBasicEngine::LoadFromFile minus the file I/O (see gps_slam_b200/checkpoint.py)"""
+        h = np.ascontiguousarray(hash_entries)
+        v = np.ascontiguousarray(voxels)
+        self.L.gsb_tsdf_load_scene.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        _check(self.L.gsb_tsdf_load_scene(self.h_, h.ctypes.data, h.size, v.ctypes.data, v.size, last_free_block, last_free_excess))
+
     def resetAll(self):
         _check(self.L.gsb_tsdf_reset(self.h_))
 

@@ -106,6 +106,13 @@ int gsb_tsdf_read(gsb_tsdf_t *e, int what, void *dst_host, size_t bytes);
 /* which: 0 lastFreeBlockId, 1 lastFreeExcessListId, 2 noVisibleEntries, 3 error flag (synchronises) */
 int gsb_tsdf_counter(gsb_tsdf_t *e, int which, int *value);
 
+/* ITMBasicEngine::LoadFromFile (Core/ITMBasicEngine.tpp:137-171) minus the file I/O: resets the engine, then installs the scene from
+ * host arrays in the reference's own layouts (hash.dat / voxel.dat payloads, lastFreeBlockId of vba.txt, lastFreeExcessListId of last.txt).
+ * SaveToFile is gsb_tsdf_read(GSB_TSDF_HASH_TABLE / GSB_TSDF_VOXELS) + gsb_tsdf_counter(0 / 1); gps_slam_b200/checkpoint.py writes and
+ * reads the reference's Scene/ directory with them. */
+int gsb_tsdf_load_scene(gsb_tsdf_t *e, const void *hash_entries_host, size_t n_entries, const void *voxels_host, size_t n_voxels,
+                        int last_free_block_id, int last_free_excess_list_id);
+
 /* Single stages on the current frame / pose, for profiling and stage-level parity.
  * stage: 0 allocate (B1-B4), 1 integrate (B5), 2 expected depth (B6), 3 raycast (B7), 4 ICP maps (B8) */
 int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage);

@@ -72,6 +72,9 @@ class ItmRef:
         for name in ("destroy", "num_hash_entries", "num_blocks", "last_free_block", "last_free_excess",
                      "tracker_result", "frames_processed"):
             getattr(L, "itmref_" + name).argtypes = [C.c_void_p]
+        for name in ("save", "load"):
+            f = getattr(L, "itmref_" + name)
+            f.argtypes = [C.c_void_p, C.c_char_p]
         self.w, self.h = intr["width"], intr["height"]
         with _quiet_stdout():
             self.h_ = L.itmref_create(self.w, self.h, intr["fx"], intr["fy"], intr["cx"], intr["cy"],
@@ -175,3 +178,15 @@ class ItmRef:
 
     def tracker_result(self):
         return self.L.itmref_tracker_result(self.h_)
+
+    def save(self, directory):
+        """ITMBasicEngine::SaveToFile: writes <directory>/Scene/{hash,excess,voxel,alloc}.dat, last.txt, vba.txt"""
+        assert directory.endswith("/")
+        with _quiet_stdout():
+            assert self.L.itmref_save(self.h_, directory.encode()) == 0
+
+    def load(self, directory):
+        """ITMBasicEngine::LoadFromFile"""
+        assert directory.endswith("/")
+        with _quiet_stdout():
+            assert self.L.itmref_load(self.h_, directory.encode()) == 0

@@ -257,4 +257,33 @@ const float *itmref_depth_level(void *h, int level, int *w, int *hh)
 	return img->GetData(MEMORYDEVICE_CPU);
 }
 
+// ITMBasicEngine::SaveToFile / LoadFromFile (Core/ITMBasicEngine.tpp:119-171); dir must end with '/'.  Returns 0 on success.
+int itmref_save(void *h, const char *dir)
+{
+	try
+	{
+		((ItmRef *)h)->engine->SaveToFile(std::string(dir));
+		return 0;
+	}
+	catch (std::exception &e)
+	{
+		fprintf(stderr, "itmref_save: %s\n", e.what());
+		return 1;
+	}
+}
+
+int itmref_load(void *h, const char *dir)
+{
+	try
+	{
+		((ItmRef *)h)->engine->LoadFromFile(std::string(dir));
+		return 0;
+	}
+	catch (std::exception &e)
+	{
+		fprintf(stderr, "itmref_load: %s\n", e.what());
+		return 1;
+	}
+}
+
 } // extern "C"
