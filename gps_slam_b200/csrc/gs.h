@@ -199,4 +199,10 @@ void ssim_fwd(int planes, int H, int W, float C1, float C2, const float *img1, c
 void ssim_bwd(int planes, int H, int W, const float *img1, const float *img2, const float *dL_dmap, const float *dm_dmu1,
               const float *dm_dsigma1_sq, const float *dm_dsigma12, float *dL_dimg1, cudaStream_t st);
 
+
+// ---- gs_knn.cu: distCUDA2 (mean squared distance to the 3 nearest other points), exact, grid based
+constexpr int KNN_MAX_CELLS = 1 << 21;
+size_t knn_workspace_bytes(int maxPoints);
+void knn_mean_dist3(int P, const float *points, float *meanDist, void *workspace, cudaStream_t st);
+
 } // namespace gs

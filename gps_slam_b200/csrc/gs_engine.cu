@@ -44,6 +44,8 @@ struct gsb_gs
     CamParams lastCam; // camera / image set of the last train step or stage-0 call (gsb_gs_run_stage)
     RasterIO lastIo;
     bool haveLast;
+    void *knnWs;     // gs_knn.cu workspace, allocated on the first gsb_gs_dist_cuda2 call
+    int knnCap;
     std::vector<void *> allocs;
 };
 
@@ -853,6 +855,26 @@ extern "C" int gsb_gs_adam_step(gsb_gs_t *e, long long n, float *param, const fl
     a.beta1 = beta1, a.beta2 = beta2, a.one_m_beta1 = (float)(1.0 - b1), a.one_m_beta2 = (float)(1.0 - b2);
     a.sqrt_bc2 = (float)sqrt(bc2), a.eps = eps;
     staged_adam((int)n, param, grad, exp_avg, exp_avg_sq, a, (float)((double)lr / bc1), e->stream);
+    GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gsb_gs_dist_cuda2(gsb_gs_t *e, int n, const float *points_dev, float *mean_dist2_dev)
+{
+    if (!e || !points_dev || !mean_dist2_dev || n <= 0)
+        return gs_set_error(__FILE__, __LINE__, "invalid argument");
+    if (!e->knnWs || n > e->knnCap)
+    {
+        // first use (or a larger point set than ever before): the one allocation this entry point makes; the old block, if any,
+        // stays on the engine's list and is released by gsb_gs_destroy
+        const int cap = n > e->cap ? n : e->cap;
+        GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+        char *ws = nullptr;
+        if (dev_alloc(e, &ws, knn_workspace_bytes(cap)))
+            return 1;
+        e->knnWs = ws, e->knnCap = cap;
+    }
+    knn_mean_dist3(n, points_dev, mean_dist2_dev, e->knnWs, e->stream);
     GS_CUDA_OK(cudaGetLastError());
     return 0;
 }

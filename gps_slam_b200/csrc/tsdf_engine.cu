@@ -45,6 +45,7 @@ struct gsb_tsdf
     icp::Tracker *tracker;
     int framesProcessed;       // ITMBasicEngine::framesProcessed (fused frames)
     int trackingFrames;        // ITMTrackingState::framesProcessed
+    bool trackingActive;       // ITMBasicEngine::trackingActive (turnOnTracking / turnOffTracking)
     int agePointCloud;         // ITMTrackingState::age_pointCloud (-1 = no valid point cloud yet)
     bool haveFrame;
     const void *lastRgba;      // RGBA frame consumed by the last ProcessFrame (own upload buffer or the caller's resident frame)
@@ -127,6 +128,7 @@ extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
     e->frame.depth_mm = e->depth_mm, e->frame.rgba = e->rgba, e->frame.depth_f = e->depth_f, e->frame.W = W, e->frame.H = H;
     e->cam.fx = cfg->fx, e->cam.fy = cfg->fy, e->cam.cx = cfg->cx, e->cam.cy = cfg->cy;
     e->tracker = nullptr;
+    e->trackingActive = cfg->tracker != 0;
     if (cfg->tracker != 0)
     {
         e->tracker = icp::create_tracker(cfg->tracker, W, H, cfg->view_frustum_min, cfg->view_frustum_max);
@@ -204,6 +206,17 @@ extern "C" int gsb_tsdf_set_stream(gsb_tsdf_t *e, void *st)
     e->stream = st ? (cudaStream_t)st : e->ownStream;
     return 0;
 }
+// ITMBasicEngine::turnOnTracking / turnOffTracking (Core/ITMBasicEngine.tpp:400-410): with tracking off ProcessFrame takes the pose
+// from gtC2wPoses[frame] (:278)
+extern "C" int gsb_tsdf_set_tracking(gsb_tsdf_t *e, int on)
+{
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    if (on && !e->tracker)
+        return gs_set_error(__FILE__, __LINE__, "engine was created without a tracker (tracker == 0)");
+    e->trackingActive = on != 0;
+    return 0;
+}
 extern "C" void *gsb_tsdf_get_stream(gsb_tsdf_t *e) { return (void *)e->stream; }
 extern "C" int gsb_tsdf_sync(gsb_tsdf_t *e)
 {
@@ -223,10 +236,10 @@ static int process_resident(gsb_tsdf *e, const float *gt_c2w)
 {
     cudaStream_t st = e->stream;
     // --- tracking (ITMBasicEngine.tpp:273-280)
-    if (e->cfg.tracker == 0)
+    if (!e->trackingActive)
     {
         if (!gt_c2w)
-            return gs_set_error(__FILE__, __LINE__, "tracker == 0 needs a ground-truth camera-to-world pose");
+            return gs_set_error(__FILE__, __LINE__, "tracking is off (tracker == 0 or gsb_tsdf_set_tracking(0)): a ground-truth camera-to-world pose is needed");
         Mat4 c2w;
         memcpy(c2w.m, gt_c2w, 64);
         e->pose_d.set_invM(c2w);

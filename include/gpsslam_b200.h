@@ -85,6 +85,9 @@ int gsb_tsdf_get_pose(gsb_tsdf_t *e, float *M, float *invM);
 int gsb_tsdf_set_pose(gsb_tsdf_t *e, const float *invM);          /* pose_d->SetInvM(invM); Coerce() */
 float gsb_tsdf_voxel_size(gsb_tsdf_t *e);
 int gsb_tsdf_frames_processed(gsb_tsdf_t *e);
+/* ITMBasicEngine::turnOnTracking / turnOffTracking (Core/ITMBasicEngine.h:91-92): off = every following ProcessFrame takes gt_c2w
+ * (createTsdfEngine with use_gt_pose, slam/InfiniTAM_tools.cpp:59-63); on needs an engine created with tracker != 0 */
+int gsb_tsdf_set_tracking(gsb_tsdf_t *e, int on);
 
 /* state read-back (synchronises).  `what`: */
 enum
@@ -287,6 +290,12 @@ int gsb_gs_ssim_fwd(gsb_gs_t *e, int planes, int height, int width, float C1, fl
                     float *ssim_map, float *dm_dmu1, float *dm_dsigma1_sq, float *dm_dsigma12);
 int gsb_gs_ssim_bwd(gsb_gs_t *e, int planes, int height, int width, const float *img1, const float *img2, const float *dL_dmap,
                     const float *dm_dmu1, const float *dm_dsigma1_sq, const float *dm_dsigma12, float *dL_dimg1);
+
+/* distCUDA2 (gsplat/rasterizer/simple_knn.cu:227-239; RawGaussianParams::init, src/raw_gs_param.cpp:28): points_dev [n,3] ->
+ * mean_dist2_dev [n] = mean of the squared distances to the 3 nearest other points (FLT_MAX terms when n < 4, as the reference).
+ * Exact (uniform grid + expanding rings instead of the reference's Morton boxes), asynchronous, no host round trip; the first call
+ * allocates its workspace (sized for max(n, capacity) points). */
+int gsb_gs_dist_cuda2(gsb_gs_t *e, int n, const float *points_dev, float *mean_dist2_dev);
 
 /* state read-back for parity tests (synchronises) */
 enum

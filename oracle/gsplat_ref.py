@@ -46,8 +46,11 @@ class RefGaussians:
     reference's optimisers (src/raw_gs_model.cpp:654-675: one Adam per tensor, eps 1e-15)."""
     KEYS = ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities")
 
-    def __init__(self, params, device="cuda", lrs=None):
+    def __init__(self, params, device="cuda", lrs=None, ops_ns=None):
+        """ops_ns: the torch.ops namespace to drive (default: the reference's own wrappers, torch.ops.gsplat_ref).  The tests pass
+        torch.ops.gsplat_b200 (the product's C++ host layer, same op schemas) to run the identical script against it."""
         import torch
+        self.ops_ns = ops_ns
         self.dev = torch.device(device)
         self.p = {k: torch.tensor(np.asarray(params[k], np.float32), device=self.dev, requires_grad=True) for k in self.KEYS}
         self.opt = None
@@ -58,7 +61,7 @@ class RefGaussians:
         """RawGaussianModel::gesForward (src/raw_gs_model.cpp:188-341); returns rgb [H,W,3], depth [H,W,1], alpha [H,W,1] and, with
         keep=True, every intermediate"""
         import torch
-        o = ops()
+        o = self.ops_ns if self.ops_ns is not None else ops()
         dev = self.dev
         def t(x):
             return x.to(dev, torch.float32) if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, np.float32), device=dev)
@@ -134,6 +137,6 @@ class RefGaussians:
         return {k: self.p[k].detach().cpu().numpy().copy() for k in self.KEYS}
 
 
-def ges_iteration(params, c2w, K, W, H, ref_depth_raw, base_color, gt_rgb, **kw):
+def ges_iteration(params, c2w, K, W, H, ref_depth_raw, base_color, gt_rgb, ops_ns=None, **kw):
     """one gesForward + loss + backward with the reference's kernels; same signature / keys as gs_oracle.ges_iteration"""
-    return RefGaussians(params).train_iteration(c2w, K, W, H, ref_depth_raw, base_color, gt_rgb, step=False, **kw)
+    return RefGaussians(params, ops_ns=ops_ns).train_iteration(c2w, K, W, H, ref_depth_raw, base_color, gt_rgb, step=False, **kw)

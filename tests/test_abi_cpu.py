@@ -35,3 +35,18 @@ def test_create_without_gpu_fails_loudly(engine_lib):
     with pytest.raises(engine.EngineError) as ei:
         engine.TsdfEngine(syn.intrinsics("replica", 0.25))
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_cxx_host_layer_builds_and_registers_the_reference_operator_names(engine_lib):
+    """gps_slam_b200/cxx (the reference-facing C++ interface over the C ABI) compiles against libtorch, loads without a GPU and
+    registers one op per wrapper of the reference's gsplat/gsplat_wapper.hpp; CPU tensors are rejected loudly (no fallback)."""
+    from gps_slam_b200 import build
+    torch.ops.load_library(build.build_torch_shim())
+    o = torch.ops.gsplat_b200
+    for name in ("fully_fused_projection", "spherical_harmonics", "isect_tiles_no_depth", "isect_offset_encode_no_depth", "isect_tiles",
+                 "isect_offset_encode", "rasterize_ges", "rasterize_ges_fwd", "rasterize_raw", "rasterize_raw_bg", "fused_ssim_map", "simple_knn"):
+        assert hasattr(o, name), name
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        o.simple_knn(torch.zeros(8, 3))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        o.fully_fused_projection(torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 3), torch.eye(4)[None], torch.eye(3)[None], 64, 64, 0.3, 0.01, 1e10, 0.0)
