@@ -10,7 +10,9 @@
     The engine never returns blocks to the free lists (no swapping, as in the SLAM configuration), so both lists stay the identity
     permutation the reference initialises them with, and the files are byte-identical to the reference's (tests/test_checkpoint_gpu.py).
 
-Pure numpy; the device side is gsb_tsdf_read / gsb_tsdf_counter / gsb_tsdf_load_scene and gsb_gs_get_params / gsb_gs_set_params."""
+  * Gaussians: the model.pt archive of RawGaussianParams::saveTensor / loadTensor (src/raw_gs_param.cpp:220-254), through libtorch.
+
+Pure numpy except model.pt; the device side is gsb_tsdf_read / gsb_tsdf_counter / gsb_tsdf_load_scene and gsb_gs_get_params / gsb_gs_set_params."""
 import os
 
 import numpy as np
@@ -53,6 +55,40 @@ def load_ply(path):
     return dict(means=rows[:, 0:3].copy(), featuresDc=rows[:, 6:9].copy(),
                 featuresRest=rows[:, 9:54].reshape(n, 3, 15).transpose(0, 2, 1).copy(), opacities=rows[:, 54:55].copy(),
                 scales=rows[:, 55:58].copy(), quats=rows[:, 58:62].copy())
+
+
+MODEL_PT_KEYS = ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities")
+
+
+def _torch_shim():
+    import torch
+    from . import build
+    torch.ops.load_library(build.build_torch_shim())
+    return torch.ops.gsplat_b200
+
+
+def save_model_pt(path, params, exposure=None, device=None):
+    """RawGaussianParams::saveTensor (reference src/raw_gs_param.cpp:220-238): the model.pt archive (torch::serialize::OutputArchive, keys
+    means / scales / quats / featuresDc / featuresRest / opacities / exposure), written through the same libtorch API by the C++ host
+    layer (cxx/gsplat_b200_ops.cpp).  params: dict of arrays or tensors in the reference's shapes; exposure defaults to the reference's
+    initial value, one 3x4 identity (src/raw_gs_param.cpp:61-65)."""
+    import torch
+    def t(a, shape):
+        x = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, np.float32))
+        x = x.detach().to(torch.float32).reshape(shape).contiguous()
+        return x.to(device) if device is not None else x
+    n = int(np.prod(np.shape(params["means"]))) // 3
+    shapes = dict(means=(n, 3), scales=(n, 3), quats=(n, 4), featuresDc=(n, 3), featuresRest=(n, 15, 3), opacities=(n, 1))
+    tensors = [t(params[k], shapes[k]) for k in MODEL_PT_KEYS]
+    tensors.append(t(exposure, (-1, 3, 4)) if exposure is not None else t(torch.eye(3, 4)[None], (1, 3, 4)))
+    _torch_shim().save_model_pt(path, tensors)
+
+
+def load_model_pt(path):
+    """RawGaussianParams::loadTensor (reference src/raw_gs_param.cpp:240-254) -> (dict of numpy arrays, exposure)"""
+    tensors = _torch_shim().load_model_pt(path)
+    out = {k: tensors[i].detach().cpu().numpy() for i, k in enumerate(MODEL_PT_KEYS)}
+    return out, tensors[6].detach().cpu().numpy()
 
 
 def _write_block(path, arr):

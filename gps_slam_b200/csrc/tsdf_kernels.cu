@@ -16,6 +16,8 @@
 //    of materialising up to 262,144 RenderingBlocks and a host-synchronised count;
 //  * the depth short->float conversion (B1) is fused into the allocation pass;
 //  * voxel blocks are streamed through shared memory with TMA bulk copies in the integrate kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tsdf.h"
 
@@ -764,31 +766,41 @@ __device__ __forceinline__ float sdf_uninterp(const Voxel *__restrict__ vba, con
     return lo_sdf(lo) / 32767.0f;
 }
 
+// The 8 corners of a trilinear read are resolved first (same order and therefore same cache / hash-walk sequence as the reference's
+// eight readVoxel calls), then all 8 voxels are requested together, then combined with the reference's arithmetic: one memory round
+// trip per interpolated read instead of four (sdf) or eight (colour) chained ones.  -1 = corner not allocated.
+__device__ __forceinline__ void find_corners(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int x, int y, int z, int &vm,
+                                             VoxelCache &c, int (&off)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+    {
+        const Voxel *v = find_voxel(vba, table, x + (k & 1), y + ((k >> 1) & 1), z + (k >> 2), vm, c);
+        off[k] = v ? (int)(v - vba) : -1;
+    }
+}
+
 template <bool withConf>
 __device__ __forceinline__ float sdf_interp(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, float3 p, int &vm, VoxelCache &c,
                                             float &conf)
 {
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     float cx = p.x - fx, cy = p.y - fy, cz = p.z - fz;
-    int x = (int)fx, y = (int)fy, z = (int)fz;
-    unsigned a, b;
+    int off[8];
+    find_corners(vba, table, (int)fx, (int)fy, (int)fz, vm, c, off);
+    unsigned lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        lo[k] = off[k] >= 0 ? __ldg(reinterpret_cast<const unsigned *>(vba + off[k])) : 0x00007fffu; // default voxel: sdf = 32767, w_depth = 0
     float res1, res2, r1c = 0, r2c = 0;
-    a = read_voxel_lo(vba, table, x, y, z, vm, c);
-    b = read_voxel_lo(vba, table, x + 1, y, z, vm, c);
-    res1 = (1.0f - cx) * lo_sdf(a) + cx * lo_sdf(b);
-    if (withConf) r1c = (1.0f - cx) * lo_w(a) + cx * lo_w(b);
-    a = read_voxel_lo(vba, table, x, y + 1, z, vm, c);
-    b = read_voxel_lo(vba, table, x + 1, y + 1, z, vm, c);
-    res1 = (1.0f - cy) * res1 + cy * ((1.0f - cx) * lo_sdf(a) + cx * lo_sdf(b));
-    if (withConf) r1c = (1.0f - cy) * r1c + cy * ((1.0f - cx) * lo_w(a) + cx * lo_w(b));
-    a = read_voxel_lo(vba, table, x, y, z + 1, vm, c);
-    b = read_voxel_lo(vba, table, x + 1, y, z + 1, vm, c);
-    res2 = (1.0f - cx) * lo_sdf(a) + cx * lo_sdf(b);
-    if (withConf) r2c = (1.0f - cx) * lo_w(a) + cx * lo_w(b);
-    a = read_voxel_lo(vba, table, x, y + 1, z + 1, vm, c);
-    b = read_voxel_lo(vba, table, x + 1, y + 1, z + 1, vm, c);
-    res2 = (1.0f - cy) * res2 + cy * ((1.0f - cx) * lo_sdf(a) + cx * lo_sdf(b));
-    if (withConf) r2c = (1.0f - cy) * r2c + cy * ((1.0f - cx) * lo_w(a) + cx * lo_w(b));
+    res1 = (1.0f - cx) * lo_sdf(lo[0]) + cx * lo_sdf(lo[1]);
+    if (withConf) r1c = (1.0f - cx) * lo_w(lo[0]) + cx * lo_w(lo[1]);
+    res1 = (1.0f - cy) * res1 + cy * ((1.0f - cx) * lo_sdf(lo[2]) + cx * lo_sdf(lo[3]));
+    if (withConf) r1c = (1.0f - cy) * r1c + cy * ((1.0f - cx) * lo_w(lo[2]) + cx * lo_w(lo[3]));
+    res2 = (1.0f - cx) * lo_sdf(lo[4]) + cx * lo_sdf(lo[5]);
+    if (withConf) r2c = (1.0f - cx) * lo_w(lo[4]) + cx * lo_w(lo[5]);
+    res2 = (1.0f - cy) * res2 + cy * ((1.0f - cx) * lo_sdf(lo[6]) + cx * lo_sdf(lo[7]));
+    if (withConf) r2c = (1.0f - cy) * r2c + cy * ((1.0f - cx) * lo_w(lo[6]) + cx * lo_w(lo[7]));
     vm = 1;
     if (withConf) conf = (1.0f - cz) * r1c + cz * r2c;
     return ((1.0f - cz) * res1 + cz * res2) / 32767.0f;
@@ -800,24 +812,24 @@ __device__ __forceinline__ uchar4 colour_interp(const Voxel *__restrict__ vba, c
     VoxelCache c = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1};
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     float cx = p.x - fx, cy = p.y - fy, cz = p.z - fz;
-    int x = (int)fx, y = (int)fy, z = (int)fz;
     float rx = 0, ry = 0, rz = 0, wsum = 0;
-    int vm;
+    int vm, off[8];
+    find_corners(vba, table, (int)fx, (int)fy, (int)fz, vm, c, off);
+    uint2 raw[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        raw[k] = off[k] >= 0 ? __ldg(reinterpret_cast<const uint2 *>(vba + off[k])) : make_uint2(0u, 0u);
 #pragma unroll
     for (int k = 0; k < 8; k++)
     {
         int ox = k & 1, oy = (k >> 1) & 1, oz = (k >> 2) & 1;
-        const Voxel *v = find_voxel(vba, table, x + ox, y + oy, z + oz, vm, c);
-        if (!v)
-            continue;
-        uint2 raw = __ldg(reinterpret_cast<const uint2 *>(v));
-        unsigned wc = (raw.y >> 16) & 0xffu;
-        if (wc >= 1u)
+        unsigned wc = (raw[k].y >> 16) & 0xffu;   // 0 for a missing corner: skipped like the reference's `continue`
+        if (off[k] >= 0 && wc >= 1u)
         {
             float w = (ox ? cx : (1.0f - cx)) * (oy ? cy : (1.0f - cy)) * (oz ? cz : (1.0f - cz));
-            rx += w * (float)((raw.x >> 24) & 0xffu);
-            ry += w * (float)(raw.y & 0xffu);
-            rz += w * (float)((raw.y >> 8) & 0xffu);
+            rx += w * (float)((raw[k].x >> 24) & 0xffu);
+            ry += w * (float)(raw[k].y & 0xffu);
+            rz += w * (float)((raw[k].y >> 8) & 0xffu);
             wsum += w;
         }
     }
@@ -832,8 +844,8 @@ __device__ __forceinline__ uchar4 colour_interp(const Voxel *__restrict__ vba, c
     return o;
 }
 
-template <bool modifyVisible, bool withColour>
-__global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay, uchar4 *__restrict__ colourOut, unsigned char *visType,
+template <bool modifyVisible, bool withColour, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_raycast(float4 *__restrict__ pointsRay, uchar4 *__restrict__ colourOut, unsigned char *visType,
                                                   const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int W, int H, Mat4 invM,
                                                   float4 invProj /* 1/fx 1/fy -cx -cy */, float oneOverVoxelSize, float mu,
                                                   const float2 *__restrict__ minmax, int mmW)
@@ -1079,15 +1091,26 @@ void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minm
     float oneOverVoxel = 1.0f / s.voxelSize;
     int mmW = cdiv(W, 8);
     GS_COUNT_LAUNCHES(1);
+    // GSB_RAYCAST_MINB=8 (experiment): 32 registers / thread -> 8 CTAs per SM instead of 6
+    static const bool dense = getenv("GSB_RAYCAST_MINB") && atoi(getenv("GSB_RAYCAST_MINB")) == 8;
+#define GSB_RAYCAST(MV, COL, MINB, colourPtr, visPtr)                                                                                           \
+    k_raycast<MV, COL, MINB><<<grid, 256, 0, st>>>(pointsRay, colourPtr, visPtr, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW)
     if (modifyVisible)
-        k_raycast<true, false><<<grid, 256, 0, st>>>(pointsRay, nullptr, s.visType, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
-                                                     mmW);
+    {
+        if (dense) GSB_RAYCAST(true, false, 8, nullptr, s.visType);
+        else GSB_RAYCAST(true, false, 6, nullptr, s.visType);
+    }
     else if (colour)
-        k_raycast<false, true><<<grid, 256, 0, st>>>(pointsRay, colour, nullptr, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
-                                                     mmW);
+    {
+        if (dense) GSB_RAYCAST(false, true, 8, colour, nullptr);
+        else GSB_RAYCAST(false, true, 6, colour, nullptr);
+    }
     else
-        k_raycast<false, false><<<grid, 256, 0, st>>>(pointsRay, nullptr, nullptr, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
-                                                      mmW);
+    {
+        if (dense) GSB_RAYCAST(false, false, 8, nullptr, nullptr);
+        else GSB_RAYCAST(false, false, 6, nullptr, nullptr);
+    }
+#undef GSB_RAYCAST
 }
 
 void icp_maps(const Scene &s, const Camera &cam, int W, int H, const float4 *pointsRay, float4 *pointsMap, float4 *normalsMap, cudaStream_t st)

@@ -86,6 +86,30 @@ Tensor fused_ssim_map(double C1, double C2, Tensor img1, Tensor img2, std::strin
 
 Tensor simple_knn(Tensor points) { return simpleKNN(points); }
 
+// RawGaussianParams::saveTensor / loadTensor (reference src/raw_gs_param.cpp:220-254): the "model.pt" checkpoint is a
+// torch::serialize archive with one named tensor per parameter.  Written with the same libtorch API, so the container format is the
+// reference's by construction; tensors are stored as given (the reference stores its CUDA tensors).
+const char *const kModelKeys[7] = {"means", "scales", "quats", "featuresDc", "featuresRest", "opacities", "exposure"};
+
+void save_model_pt(std::string filename, Tensors params)
+{
+    TORCH_CHECK(params.size() == 7, "expected means, scales, quats, featuresDc, featuresRest, opacities, exposure");
+    torch::serialize::OutputArchive archive;
+    for (int i = 0; i < 7; i++)
+        archive.write(kModelKeys[i], params[i]);
+    archive.save_to(filename);
+}
+
+Tensors load_model_pt(std::string filename)
+{
+    torch::serialize::InputArchive archive;
+    archive.load_from(filename);
+    Tensors params(7);
+    for (int i = 0; i < 7; i++)
+        archive.read(kModelKeys[i], params[i]);
+    return params;
+}
+
 } // namespace
 
 TORCH_LIBRARY(gsplat_b200, m)
@@ -102,4 +126,6 @@ TORCH_LIBRARY(gsplat_b200, m)
     m.def("rasterize_raw_bg", &rasterize_raw_bg);
     m.def("fused_ssim_map", &fused_ssim_map);
     m.def("simple_knn", &simple_knn);
+    m.def("save_model_pt", &save_model_pt);
+    m.def("load_model_pt", &load_model_pt);
 }
