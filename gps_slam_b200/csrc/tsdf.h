@@ -40,6 +40,7 @@ void allocate(const Scene &s, const Frame &f, const Camera &cam, cudaStream_t st
 void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, cudaStream_t st);
 void expected_depth_live(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st);
 void expected_depth_free(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st);
+void raycast_stats(const Scene &s, const Camera &cam, int W, int H, const float2 *minmax, unsigned long long *totals8, cudaStream_t st);
 void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minmax, float4 *pointsRay, uchar4 *colour, bool modifyVisible,
              cudaStream_t st);
 void icp_maps(const Scene &s, const Camera &cam, int W, int H, const float4 *pointsRay, float4 *pointsMap, float4 *normalsMap, cudaStream_t st);

@@ -324,6 +324,31 @@ extern "C" int gsb_tsdf_run_raycast(gsb_tsdf_t *e, const float *c2w, float fx, f
     return 0;
 }
 
+// diagnostic: march statistics of a free-view raycast from c2w (does not touch the free-view outputs); synchronises
+extern "C" int gsb_tsdf_raycast_stats(gsb_tsdf_t *e, const float *c2w, float fx, float fy, float cx, float cy, unsigned long long *totals8_host)
+{
+    if (!e || !c2w || !totals8_host)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    se3::Pose p;
+    Mat4 m;
+    memcpy(m.m, c2w, 64);
+    p.set_invM(m);
+    tsdf::Camera cam;
+    cam.M = p.M;
+    cam.invM = p.get_invM();
+    cam.fx = fx, cam.fy = fy, cam.cx = cx, cam.cy = cy;
+    const int W = e->cfg.width, H = e->cfg.height;
+    unsigned long long *tot = nullptr;
+    E_CUDA(cudaMalloc((void **)&tot, 64));
+    E_CUDA(cudaMemsetAsync(tot, 0, 64, e->stream));
+    tsdf::expected_depth_free(e->scene, cam, W, H, e->minmaxFree, e->stream);
+    tsdf::raycast_stats(e->scene, cam, W, H, e->minmaxFree, tot, e->stream);
+    E_CUDA(cudaMemcpyAsync(totals8_host, tot, 64, cudaMemcpyDeviceToHost, e->stream));
+    E_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(tot);
+    return 0;
+}
+
 extern "C" const void *gsb_tsdf_current_rgba_dev(gsb_tsdf_t *e) { return e->lastRgba; }
 extern "C" const void *gsb_tsdf_free_image_dev(gsb_tsdf_t *e) { return e->imageFree; }
 extern "C" const void *gsb_tsdf_free_vertex_dev(gsb_tsdf_t *e) { return e->rayFree; }

@@ -772,8 +772,19 @@ __device__ __forceinline__ float sdf_uninterp(const Voxel *__restrict__ vba, con
 __device__ __forceinline__ void find_corners(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int x, int y, int z, int &vm,
                                              VoxelCache &c, int (&off)[8])
 {
+    const Voxel *v0 = find_voxel(vba, table, x, y, z, vm, c);
+    off[0] = v0 ? (int)(v0 - vba) : -1;
+    if (((x & 7) != 7) && ((y & 7) != 7) && ((z & 7) != 7))
+    {
+        // all 8 corners lie in the block of corner 0 (2 reads out of 3): the seven remaining readVoxel calls would be cache hits on it
+        // (or walk the same empty hash chain) without changing any state, so their addresses follow from the first
 #pragma unroll
-    for (int k = 0; k < 8; k++)
+        for (int k = 1; k < 8; k++)
+            off[k] = v0 ? off[0] + (k & 1) + ((k >> 1) & 1) * SDF_BLOCK_SIZE + (k >> 2) * SDF_BLOCK_SIZE * SDF_BLOCK_SIZE : -1;
+        return;
+    }
+#pragma unroll
+    for (int k = 1; k < 8; k++)
     {
         const Voxel *v = find_voxel(vba, table, x + (k & 1), y + ((k >> 1) & 1), z + (k >> 2), vm, c);
         off[k] = v ? (int)(v - vba) : -1;
@@ -844,7 +855,9 @@ __device__ __forceinline__ uchar4 colour_interp(const Voxel *__restrict__ vba, c
     return o;
 }
 
-template <bool modifyVisible, bool withColour, int MINB>
+// STATS (diagnostic build of the same loop, gsb_tsdf_raycast_stats): visType is reinterpreted as unsigned long long[8] totals --
+// rays, march steps, steps in unallocated space, trilinear reads, steps that changed voxel block, warp-max steps summed over warps, warps
+template <bool modifyVisible, bool withColour, int MINB, bool STATS = false>
 __global__ void __launch_bounds__(256, MINB) k_raycast(float4 *__restrict__ pointsRay, uchar4 *__restrict__ colourOut, unsigned char *visType,
                                                   const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int W, int H, Mat4 invM,
                                                   float4 invProj /* 1/fx 1/fy -cx -cy */, float oneOverVoxelSize, float mu,
@@ -883,16 +896,30 @@ __global__ void __launch_bounds__(256, MINB) k_raycast(float4 *__restrict__ poin
     VoxelCache cache = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1};
     float sdf = 1.0f, conf = 0.0f, stepLength;
     int vm;
+    int nSteps = 0, nMiss = 0, nInterp = 0, nBlock = 0;
+    bool hitSlot0 = false;
     while (totalLength < totalLengthMax)
     {
         sdf = sdf_uninterp(vba, table, pt, vm, cache);
+        if (STATS)
+            nSteps++, nMiss += (vm == 0), nBlock += (vm > 1);
         if (modifyVisible)
-            if (vm)
-                visType[vm - 1] = 1; // NB: a cache hit reports vm == 1, i.e. slot 0 -- reference quirk kept (Access.h:86-90)
+        {
+            // NB: a cache hit reports vm == 1, i.e. slot 0 -- reference quirk kept (Access.h:86-90).  Nearly every step of every ray is
+            // such a hit: the write to slot 0 is remembered and issued once per warp after the march instead of ~6 M times to one address
+            // (the L2 slice owning that sector serialised them and every load behind them waited: 5x the long-scoreboard stall of the
+            // free-view variant)
+            if (vm > 1)
+                visType[vm - 1] = 1;
+            else if (vm == 1)
+                hitSlot0 = true;
+        }
         if (!vm)
             stepLength = SDF_BLOCK_SIZE;
         else
         {
+            if (STATS)
+                nInterp += ((sdf <= 0.1f) && (sdf >= -0.5f));
             if ((sdf <= 0.1f) && (sdf >= -0.5f))
                 sdf = sdf_interp<false>(vba, table, pt, vm, cache, conf);
             if (sdf <= 0.0f)
@@ -901,6 +928,12 @@ __global__ void __launch_bounds__(256, MINB) k_raycast(float4 *__restrict__ poin
         }
         pt.x += stepLength * rd.x, pt.y += stepLength * rd.y, pt.z += stepLength * rd.z;
         totalLength += stepLength;
+    }
+    if (modifyVisible)
+    {
+        const unsigned act = __activemask();
+        if (__any_sync(act, hitSlot0) && lane == __ffs(act) - 1)
+            visType[0] = 1;
     }
     bool found;
     if (sdf <= 0.0f)
@@ -915,6 +948,19 @@ __global__ void __launch_bounds__(256, MINB) k_raycast(float4 *__restrict__ poin
     else
         found = false;
     int loc = x + y * W;
+    if (STATS)
+    {
+        unsigned long long *tot = reinterpret_cast<unsigned long long *>(visType);
+        const unsigned act = __activemask();
+        int warpMax = nSteps;
+        for (int o = 16; o; o >>= 1)
+            warpMax = max(warpMax, __shfl_xor_sync(act, warpMax, o));
+        atomicAdd(tot + 0, 1ull), atomicAdd(tot + 1, (unsigned long long)nSteps), atomicAdd(tot + 2, (unsigned long long)nMiss);
+        atomicAdd(tot + 3, (unsigned long long)nInterp), atomicAdd(tot + 4, (unsigned long long)nBlock);
+        if (lane == __ffs(act) - 1)
+            atomicAdd(tot + 5, (unsigned long long)warpMax), atomicAdd(tot + 6, 1ull);
+        return;
+    }
     pointsRay[loc] = make_float4(pt.x, pt.y, pt.z, found ? conf + 1.0f : 0.0f);
     if (withColour)
     {
@@ -1111,6 +1157,16 @@ void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minm
         else GSB_RAYCAST(false, false, 6, nullptr, nullptr);
     }
 #undef GSB_RAYCAST
+}
+
+// diagnostic: the free-view march with step counters instead of outputs; totals8 = device unsigned long long[8], zeroed by the caller
+void raycast_stats(const Scene &s, const Camera &cam, int W, int H, const float2 *minmax, unsigned long long *totals8, cudaStream_t st)
+{
+    dim3 grid(cdiv(W, 32), cdiv(H, 8));
+    float4 invProj = make_float4(1.0f / cam.fx, 1.0f / cam.fy, -cam.cx, -cam.cy);
+    GS_COUNT_LAUNCHES(1);
+    k_raycast<false, false, 6, true><<<grid, 256, 0, st>>>(nullptr, nullptr, reinterpret_cast<unsigned char *>(totals8), s.vba, s.table, W, H, cam.invM,
+                                                          invProj, 1.0f / s.voxelSize, s.mu, minmax, cdiv(W, 8));
 }
 
 void icp_maps(const Scene &s, const Camera &cam, int W, int H, const float4 *pointsRay, float4 *pointsMap, float4 *normalsMap, cudaStream_t st)

@@ -80,6 +80,11 @@ const void *gsb_tsdf_live_vertex_dev(gsb_tsdf_t *e);  /* GetLiveVertex()        
 const void *gsb_tsdf_points_map_dev(gsb_tsdf_t *e);   /* trackingState->pointCloud->locations (metres, w=conf+1/-1)  */
 const void *gsb_tsdf_normals_map_dev(gsb_tsdf_t *e);  /* trackingState->pointCloud->colours                          */
 
+/* diagnostic (tools/raycast_stats.py): march statistics of a free-view raycast from c2w -- totals8_host = rays, march steps, steps through
+ * unallocated space, trilinear reads, steps that entered another voxel block, sum over warps of the slowest ray's steps, warps, 0.
+ * Leaves the free-view outputs untouched; synchronises. */
+int gsb_tsdf_raycast_stats(gsb_tsdf_t *e, const float *c2w, float fx, float fy, float cx, float cy, unsigned long long *totals8_host);
+
 /* GetTrackingState()->pose_d: M = GetM() (world->camera), invM = GetInvM() */
 int gsb_tsdf_get_pose(gsb_tsdf_t *e, float *M, float *invM);
 int gsb_tsdf_set_pose(gsb_tsdf_t *e, const float *invM);          /* pose_d->SetInvM(invM); Coerce() */
