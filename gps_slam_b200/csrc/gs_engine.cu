@@ -54,6 +54,9 @@ static int dev_alloc(gsb_gs *e, T **p, size_t n)
 {
     GS_CUDA_OK(cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)));
     e->allocs.push_back((void *)*p);
+    // cudaMalloc hands back recycled, uncleared memory: every buffer starts from zero so that nothing (dropped work items after a
+    // capacity overflow, padding rows past the Gaussian count) can ever depend on what a previous owner left there
+    GS_CUDA_OK(cudaMemset((void *)*p, 0, (n ? n : 1) * sizeof(T)));
     return 0;
 }
 

@@ -170,7 +170,12 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
                 items[base + i] = make_int4(g, i * BWD_PIXELS_PER_ITEM, rectXY, rectWH);
         }
         else
+        {
+            // dropped work items: nothing will write this splat's raster gradient -> it is zero, not whatever the buffer held
             atomicOr(&counters[CNT_OVERFLOW], 2);
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            grads[g].g0 = z, grads[g].g1 = z, grads[g].g2 = z;
+        }
     }
     if (!inRange)
         return;

@@ -192,7 +192,11 @@ __global__ void __launch_bounds__(256) k_staged_pack(int N, const float *__restr
                 for (int i = 0; i < nItems; i++)
                     items[base + i] = make_int4(g, i * BWD_PIXELS_PER_ITEM, rx | (ry << 16), rw | (rh << 16));
             else
+            {
                 atomicOr(&counters[CNT_OVERFLOW], 2);
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                grads[g].g0 = z, grads[g].g1 = z, grads[g].g2 = z;
+            }
         }
     }
     SplatRec rec;
