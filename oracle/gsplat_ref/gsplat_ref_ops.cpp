@@ -88,6 +88,32 @@ TensorList rasterize_ges_fwd(Tensor means2d, Tensor conics, Tensor colors, Tenso
     return {std::get<0>(r), std::get<1>(r), std::get<2>(r)};
 }
 
+// the backward kernel alone, WITH the background term (rasterize_to_pixels_bwd.cu:289-511).  The autograd wrapper above never passes
+// the background to it (gsplat_wapper.hpp:300-312: `backgrounds` is a fresh empty optional in backward), so the wrapper's gradients
+// are those of the background-free composite; this entry exposes what the kernel computes when it is given one.
+TensorList rasterize_raw_bwd(Tensor means2d, Tensor conics, Tensor colors, Tensor opacities, Tensor backgrounds, int64_t width, int64_t height,
+                             int64_t tile_size, Tensor isect_offsets, Tensor flatten_ids, Tensor render_alphas, Tensor last_ids,
+                             Tensor v_render_colors, Tensor v_render_alphas)
+{
+    at::optional<Tensor> none, bg = backgrounds.contiguous();
+    auto r = gsplat::rasterize_to_pixels_bwd_tensor(means2d.contiguous(), conics.contiguous(), colors.contiguous(), opacities.contiguous(), bg, none,
+                                                    (uint32_t)width, (uint32_t)height, (uint32_t)tile_size, isect_offsets.contiguous(),
+                                                    flatten_ids.contiguous(), render_alphas.contiguous(), last_ids.contiguous(),
+                                                    v_render_colors.contiguous(), v_render_alphas.contiguous(), false);
+    return {std::get<1>(r), std::get<2>(r), std::get<3>(r), std::get<4>(r)};
+}
+
+// the forward kernel alone (returns last_ids too): rasterize_to_pixels_fwd.cu:198-376
+TensorList rasterize_raw_fwd(Tensor means2d, Tensor conics, Tensor colors, Tensor opacities, Tensor backgrounds, int64_t width, int64_t height,
+                             int64_t tile_size, Tensor isect_offsets, Tensor flatten_ids)
+{
+    at::optional<Tensor> none, bg = backgrounds.contiguous();
+    auto r = gsplat::rasterize_to_pixels_fwd_tensor(means2d.contiguous(), conics.contiguous(), colors.contiguous(), opacities.contiguous(), bg, none,
+                                                    (uint32_t)width, (uint32_t)height, (uint32_t)tile_size, isect_offsets.contiguous(),
+                                                    flatten_ids.contiguous());
+    return {std::get<0>(r), std::get<1>(r), std::get<2>(r)};
+}
+
 // gsplat_wapper.hpp:622-676
 Tensor fused_ssim_map(double C1, double C2, Tensor img1, Tensor img2, std::string padding, bool train)
 {
@@ -111,6 +137,8 @@ TORCH_LIBRARY(gsplat_ref, m)
     m.def("rasterize_ges_fwd", &rasterize_ges_fwd);
     m.def("rasterize_raw", &rasterize_raw);
     m.def("rasterize_raw_bg", &rasterize_raw_bg);
+    m.def("rasterize_raw_fwd", &rasterize_raw_fwd);
+    m.def("rasterize_raw_bwd", &rasterize_raw_bwd);
     m.def("fused_ssim_map", &fused_ssim_map);
     m.def("simple_knn", &simple_knn);
 }

@@ -52,10 +52,20 @@ def test_raw_rasteriser_matches_reference(engine_lib, gsref, N, W, H, seed, kw, 
         gc.close_frac("alphas", n(alpha), n(r_alpha), 3e-4, 3e-4, 3e-4)
         # ---- backward
         v_render, v_alpha = torch.randn(1, H, W, 4, device=DEV, generator=g) * 1e-3, torch.randn(1, H, W, 1, device=DEV, generator=g) * 1e-3
+        # RasterizeToPixels::backward never hands the background to the kernel (gsplat_wapper.hpp:300-312 there: a fresh empty optional),
+        # so the reference's autograd gives the gradients of the background-free composite: compared with ours WITHOUT a background
         rv = torch.autograd.grad([r_render, r_alpha], ins, [v_render, v_alpha])
-        mine = ops.rasterize_to_pixels_bwd(m2d, conics, colors4, opac, bg_t, r_off, r_flat, alpha, last, v_render, v_alpha)
+        mine = ops.rasterize_to_pixels_bwd(m2d, conics, colors4, opac, None, r_off, r_flat, alpha, last, v_render, v_alpha)
         for name, a, b in zip(("v_means2d", "v_conics", "v_colors", "v_opacities"), mine, rv):
             gc.close_scaled(name, n(a).reshape(N, -1)[vis], n(b).reshape(N, -1)[vis], 3e-3, 2e-4)
+        if bg:
+            # ... and the kernel itself given the background (rasterize_to_pixels_bwd_tensor), against ours WITH it
+            r_last = gsref.rasterize_raw_fwd(m2d, conics, colors4, opac, bg_t, W, H, 16, r_off, r_flat)[2]
+            rk = gsref.rasterize_raw_bwd(m2d, conics, colors4, opac, bg_t, W, H, 16, r_off, r_flat, r_alpha.detach(), r_last, v_render, v_alpha)
+            mine_bg = ops.rasterize_to_pixels_bwd(m2d, conics, colors4, opac, bg_t, r_off, r_flat, alpha, last, v_render, v_alpha)
+            for name, a, b in zip(("v_means2d", "v_conics", "v_colors", "v_opacities"), mine_bg, rk):
+                gc.close_scaled(name + " (background)", n(a).reshape(N, -1)[vis], n(b).reshape(N, -1)[vis], 3e-3, 2e-4)
+            assert np.abs(n(mine_bg[0]) - n(mine[0])).max() > 0      # the term is not a no-op on this scene
     finally:
         ops.close()
 
