@@ -9,6 +9,8 @@
 #include <vector>
 
 #include "../../include/gpsslam_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "icp.h"
 #include "se3.h"
@@ -89,6 +91,8 @@ extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
     if (!e)
         return gs_set_error(__FILE__, __LINE__, "out of host memory");
     e->cfg = *cfg;
+    if (const char *v = getenv("GSB_INTEGRATE_VARIANT"))   // experiments: override the integrate kernel variant of every engine
+        e->cfg.integrate_variant = atoi(v);
     if (e->cfg.num_blocks <= 0)
         e->cfg.num_blocks = SDF_DEFAULT_BLOCK_NUM;
     if (e->cfg.max_w <= 0)
