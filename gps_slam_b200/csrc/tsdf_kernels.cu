@@ -987,8 +987,8 @@ __device__ __forceinline__ uchar4 colour_interp(const Voxel *__restrict__ vba, c
 
 // STATS (diagnostic build of the same loop, gsb_tsdf_raycast_stats): visType is reinterpreted as unsigned long long[8] totals --
 // rays, march steps, steps in unallocated space, trilinear reads, steps that changed voxel block, warp-max steps summed over warps, warps
-template <bool modifyVisible, bool withColour, int MINB, bool STATS = false>
-__global__ void __launch_bounds__(256, MINB) k_raycast(float4 *__restrict__ pointsRay, uchar4 *__restrict__ colourOut, unsigned char *visType,
+template <bool modifyVisible, bool withColour, bool STATS = false>
+__global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay, uchar4 *__restrict__ colourOut, unsigned char *visType,
                                                   const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int W, int H, Mat4 invM,
                                                   float4 invProj /* 1/fx 1/fy -cx -cy */, float oneOverVoxelSize, float mu,
                                                   const float2 *__restrict__ minmax, int mmW)
@@ -1269,26 +1269,16 @@ void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minm
     float oneOverVoxel = 1.0f / s.voxelSize;
     int mmW = cdiv(W, 8);
     GS_COUNT_LAUNCHES(1);
-    // GSB_RAYCAST_MINB=8 (experiment): 32 registers / thread -> 8 CTAs per SM instead of 6
-    static const bool dense = getenv("GSB_RAYCAST_MINB") && atoi(getenv("GSB_RAYCAST_MINB")) == 8;
-#define GSB_RAYCAST(MV, COL, MINB, colourPtr, visPtr)                                                                                           \
-    k_raycast<MV, COL, MINB><<<grid, 256, 0, st>>>(pointsRay, colourPtr, visPtr, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW)
+    // (forcing 32 registers / thread for 8 CTAs per SM was measured: no gain, the kernel is issue-bound)
     if (modifyVisible)
-    {
-        if (dense) GSB_RAYCAST(true, false, 8, nullptr, s.visType);
-        else GSB_RAYCAST(true, false, 6, nullptr, s.visType);
-    }
+        k_raycast<true, false><<<grid, 256, 0, st>>>(pointsRay, nullptr, s.visType, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
+                                                     mmW);
     else if (colour)
-    {
-        if (dense) GSB_RAYCAST(false, true, 8, colour, nullptr);
-        else GSB_RAYCAST(false, true, 6, colour, nullptr);
-    }
+        k_raycast<false, true><<<grid, 256, 0, st>>>(pointsRay, colour, nullptr, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
+                                                     mmW);
     else
-    {
-        if (dense) GSB_RAYCAST(false, false, 8, nullptr, nullptr);
-        else GSB_RAYCAST(false, false, 6, nullptr, nullptr);
-    }
-#undef GSB_RAYCAST
+        k_raycast<false, false><<<grid, 256, 0, st>>>(pointsRay, nullptr, nullptr, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
+                                                      mmW);
 }
 
 // diagnostic: the free-view march with step counters instead of outputs; totals8 = device unsigned long long[8], zeroed by the caller
@@ -1297,7 +1287,7 @@ void raycast_stats(const Scene &s, const Camera &cam, int W, int H, const float2
     dim3 grid(cdiv(W, 32), cdiv(H, 8));
     float4 invProj = make_float4(1.0f / cam.fx, 1.0f / cam.fy, -cam.cx, -cam.cy);
     GS_COUNT_LAUNCHES(1);
-    k_raycast<false, false, 6, true><<<grid, 256, 0, st>>>(nullptr, nullptr, reinterpret_cast<unsigned char *>(totals8), s.vba, s.table, W, H, cam.invM,
+    k_raycast<false, false, true><<<grid, 256, 0, st>>>(nullptr, nullptr, reinterpret_cast<unsigned char *>(totals8), s.vba, s.table, W, H, cam.invM,
                                                           invProj, 1.0f / s.voxelSize, s.mu, minmax, cdiv(W, 8));
 }
 
