@@ -50,3 +50,28 @@ def test_cxx_host_layer_builds_and_registers_the_reference_operator_names(engine
         o.simple_knn(torch.zeros(8, 3))
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         o.fully_fused_projection(torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 3), torch.eye(4)[None], torch.eye(3)[None], 64, 64, 0.3, 0.01, 1e10, 0.0)
+
+
+REF_SLAM = "/root/reference/slam"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SLAM), reason="the reference tree is only mounted in the build container")
+def test_reference_cliengine_compiles_unchanged_against_the_itm_facade(tmp_path):
+    """slam/TsdfFusion/CLIEngine.cpp of the reference (its frame loop around ITMMainEngine::ProcessFrame), compiled where it lies with
+    the facade headers of gps_slam_b200/cxx/InfiniTAM in place of the reference's InfiniTAM/ include directory"""
+    import subprocess
+    from gps_slam_b200 import build
+    inc, _ = build.itm_facade_flags()
+    obj = str(tmp_path / "cliengine.o")
+    r = subprocess.run(["g++", "-std=c++17", "-c"] + inc + ["-I", REF_SLAM, os.path.join(REF_SLAM, "TsdfFusion", "CLIEngine.cpp"), "-o", obj],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    assert "InfiniTAM::Engine::CLIEngine::ProcessFrame()" in syms and "InfiniTAM::Engine::CLIEngine::Initialise" in syms
+
+
+def test_itm_facade_driver_builds(engine_lib):
+    """the C++ program that drives the TSDF / ICP engine through the facade (tests/cxx/itm_facade_driver.cpp) builds and links"""
+    from gps_slam_b200 import build
+    exe = build.build_itm_driver()
+    assert os.access(exe, os.X_OK)
