@@ -415,6 +415,35 @@ __device__ __forceinline__ void tma_store_wait_read()
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- exact fp32 division by the small set of divisors integrate_voxel meets, without the ~12-instruction IEEE division sequence.
+// For a divisor c with r = RN(1/c):  q = x * r;  q' = fma(fma(-q, c, x), r, q)  is the correctly rounded x / c.  Proven by exhaustion on the
+// CPU (IEEE fmaf, every fp32 bit pattern of x): c = 255 and c = 32767 for ALL x except -0 and +-inf (unreachable here: the numerators
+// are sums of non-negative products or integer conversions); every integer c in 1..256 for 2^-80 <= |x| < 2^11 (outside that range the
+// plain division is used).  The quotients, and with them the voxels, stay bit-identical to the reference's.
+__device__ __forceinline__ float div_255(float x)
+{
+    const float q = __fmul_rn(x, 0x1.010102p-8f);
+    return __fmaf_rn(__fmaf_rn(-q, 255.0f, x), 0x1.010102p-8f, q);
+}
+__device__ __forceinline__ float div_32767(float x)
+{
+    const float q = __fmul_rn(x, 0x1.0002p-15f);
+    return __fmaf_rn(__fmaf_rn(-q, 32767.0f, x), 0x1.0002p-15f, q);
+}
+// RN(1 / w) for w = 0..256 (entry 0 unused)
+__device__ const float c_rcpInt[257] = {0.0f, 0x1.0000000000000p+0f, 0x1.0000000000000p-1f, 0x1.5555560000000p-2f, 0x1.0000000000000p-2f, 0x1.99999a0000000p-3f, 0x1.5555560000000p-3f, 0x1.24924a0000000p-3f, 0x1.0000000000000p-3f, 0x1.c71c720000000p-4f, 0x1.99999a0000000p-4f, 0x1.745d180000000p-4f, 0x1.5555560000000p-4f, 0x1.3b13b20000000p-4f, 0x1.24924a0000000p-4f, 0x1.1111120000000p-4f, 0x1.0000000000000p-4f, 0x1.e1e1e20000000p-5f, 0x1.c71c720000000p-5f, 0x1.af286c0000000p-5f, 0x1.99999a0000000p-5f, 0x1.8618620000000p-5f, 0x1.745d180000000p-5f, 0x1.642c860000000p-5f, 0x1.5555560000000p-5f, 0x1.47ae140000000p-5f, 0x1.3b13b20000000p-5f, 0x1.2f684c0000000p-5f, 0x1.24924a0000000p-5f, 0x1.1a7b960000000p-5f, 0x1.1111120000000p-5f, 0x1.0842100000000p-5f, 0x1.0000000000000p-5f, 0x1.f07c200000000p-6f, 0x1.e1e1e20000000p-6f, 0x1.d41d420000000p-6f, 0x1.c71c720000000p-6f, 0x1.bacf920000000p-6f, 0x1.af286c0000000p-6f, 0x1.a41a420000000p-6f, 0x1.99999a0000000p-6f, 0x1.8f9c180000000p-6f, 0x1.8618620000000p-6f, 0x1.7d05f40000000p-6f, 0x1.745d180000000p-6f, 0x1.6c16c20000000p-6f, 0x1.642c860000000p-6f, 0x1.5c98820000000p-6f, 0x1.5555560000000p-6f, 0x1.4e5e0a0000000p-6f, 0x1.47ae140000000p-6f, 0x1.4141420000000p-6f, 0x1.3b13b20000000p-6f, 0x1.3521d00000000p-6f, 0x1.2f684c0000000p-6f, 0x1.29e4120000000p-6f, 0x1.24924a0000000p-6f, 0x1.1f70480000000p-6f, 0x1.1a7b960000000p-6f, 0x1.15b1e60000000p-6f, 0x1.1111120000000p-6f, 0x1.0c97140000000p-6f, 0x1.0842100000000p-6f, 0x1.0410420000000p-6f, 0x1.0000000000000p-6f, 0x1.f81f820000000p-7f, 0x1.f07c200000000p-7f, 0x1.e9131a0000000p-7f, 0x1.e1e1e20000000p-7f, 0x1.dae6080000000p-7f, 0x1.d41d420000000p-7f, 0x1.cd85680000000p-7f, 0x1.c71c720000000p-7f, 0x1.c0e0700000000p-7f, 0x1.bacf920000000p-7f, 0x1.b4e81c0000000p-7f, 0x1.af286c0000000p-7f, 0x1.a98ef60000000p-7f, 0x1.a41a420000000p-7f, 0x1.9ec8ea0000000p-7f, 0x1.99999a0000000p-7f, 0x1.948b100000000p-7f, 0x1.8f9c180000000p-7f, 0x1.8acb900000000p-7f, 0x1.8618620000000p-7f, 0x1.8181820000000p-7f, 0x1.7d05f40000000p-7f, 0x1.78a4c80000000p-7f, 0x1.745d180000000p-7f, 0x1.702e060000000p-7f, 0x1.6c16c20000000p-7f, 0x1.6816820000000p-7f, 0x1.642c860000000p-7f, 0x1.6058160000000p-7f, 0x1.5c98820000000p-7f, 0x1.58ed240000000p-7f, 0x1.5555560000000p-7f, 0x1.51d07e0000000p-7f, 0x1.4e5e0a0000000p-7f, 0x1.4afd6a0000000p-7f, 0x1.47ae140000000p-7f, 0x1.446f860000000p-7f, 0x1.4141420000000p-7f, 0x1.3e22cc0000000p-7f, 0x1.3b13b20000000p-7f, 0x1.3813820000000p-7f, 0x1.3521d00000000p-7f, 0x1.323e340000000p-7f, 0x1.2f684c0000000p-7f, 0x1.2c9fb40000000p-7f, 0x1.29e4120000000p-7f, 0x1.27350c0000000p-7f, 0x1.24924a0000000p-7f, 0x1.21fb780000000p-7f, 0x1.1f70480000000p-7f, 0x1.1cf06a0000000p-7f, 0x1.1a7b960000000p-7f, 0x1.1811820000000p-7f, 0x1.15b1e60000000p-7f, 0x1.135c820000000p-7f, 0x1.1111120000000p-7f, 0x1.0ecf560000000p-7f, 0x1.0c97140000000p-7f, 0x1.0a68100000000p-7f, 0x1.0842100000000p-7f, 0x1.0624de0000000p-7f, 0x1.0410420000000p-7f, 0x1.0204080000000p-7f, 0x1.0000000000000p-7f, 0x1.fc07f00000000p-8f, 0x1.f81f820000000p-8f, 0x1.f4465a0000000p-8f, 0x1.f07c200000000p-8f, 0x1.ecc07c0000000p-8f, 0x1.e9131a0000000p-8f, 0x1.e573ac0000000p-8f, 0x1.e1e1e20000000p-8f, 0x1.de5d6e0000000p-8f, 0x1.dae6080000000p-8f, 0x1.d77b660000000p-8f, 0x1.d41d420000000p-8f, 0x1.d0cb580000000p-8f, 0x1.cd85680000000p-8f, 0x1.ca4b300000000p-8f, 0x1.c71c720000000p-8f, 0x1.c3f8f00000000p-8f, 0x1.c0e0700000000p-8f, 0x1.bdd2b80000000p-8f, 0x1.bacf920000000p-8f, 0x1.b7d6c40000000p-8f, 0x1.b4e81c0000000p-8f, 0x1.b203640000000p-8f, 0x1.af286c0000000p-8f, 0x1.ac57020000000p-8f, 0x1.a98ef60000000p-8f, 0x1.a6d01a0000000p-8f, 0x1.a41a420000000p-8f, 0x1.a16d400000000p-8f, 0x1.9ec8ea0000000p-8f, 0x1.9c2d140000000p-8f, 0x1.99999a0000000p-8f, 0x1.970e500000000p-8f, 0x1.948b100000000p-8f, 0x1.920fb40000000p-8f, 0x1.8f9c180000000p-8f, 0x1.8d30180000000p-8f, 0x1.8acb900000000p-8f, 0x1.886e600000000p-8f, 0x1.8618620000000p-8f, 0x1.83c9780000000p-8f, 0x1.8181820000000p-8f, 0x1.7f40600000000p-8f, 0x1.7d05f40000000p-8f, 0x1.7ad2200000000p-8f, 0x1.78a4c80000000p-8f, 0x1.767dce0000000p-8f, 0x1.745d180000000p-8f, 0x1.7242880000000p-8f, 0x1.702e060000000p-8f, 0x1.6e1f760000000p-8f, 0x1.6c16c20000000p-8f, 0x1.6a13ce0000000p-8f, 0x1.6816820000000p-8f, 0x1.661ec60000000p-8f, 0x1.642c860000000p-8f, 0x1.623fa80000000p-8f, 0x1.6058160000000p-8f, 0x1.5e75bc0000000p-8f, 0x1.5c98820000000p-8f, 0x1.5ac0560000000p-8f, 0x1.58ed240000000p-8f, 0x1.571ed40000000p-8f, 0x1.5555560000000p-8f, 0x1.5390940000000p-8f, 0x1.51d07e0000000p-8f, 0x1.5015020000000p-8f, 0x1.4e5e0a0000000p-8f, 0x1.4cab880000000p-8f, 0x1.4afd6a0000000p-8f, 0x1.49539e0000000p-8f, 0x1.47ae140000000p-8f, 0x1.460cbc0000000p-8f, 0x1.446f860000000p-8f, 0x1.42d6620000000p-8f, 0x1.4141420000000p-8f, 0x1.3fb0140000000p-8f, 0x1.3e22cc0000000p-8f, 0x1.3c995a0000000p-8f, 0x1.3b13b20000000p-8f, 0x1.3991c20000000p-8f, 0x1.3813820000000p-8f, 0x1.3698e00000000p-8f, 0x1.3521d00000000p-8f, 0x1.33ae460000000p-8f, 0x1.323e340000000p-8f, 0x1.30d1900000000p-8f, 0x1.2f684c0000000p-8f, 0x1.2e025c0000000p-8f, 0x1.2c9fb40000000p-8f, 0x1.2b404a0000000p-8f, 0x1.29e4120000000p-8f, 0x1.288b020000000p-8f, 0x1.27350c0000000p-8f, 0x1.25e2280000000p-8f, 0x1.24924a0000000p-8f, 0x1.2345680000000p-8f, 0x1.21fb780000000p-8f, 0x1.20b4700000000p-8f, 0x1.1f70480000000p-8f, 0x1.1e2ef40000000p-8f, 0x1.1cf06a0000000p-8f, 0x1.1bb4a40000000p-8f, 0x1.1a7b960000000p-8f, 0x1.1945380000000p-8f, 0x1.1811820000000p-8f, 0x1.16e0680000000p-8f, 0x1.15b1e60000000p-8f, 0x1.1485f00000000p-8f, 0x1.135c820000000p-8f, 0x1.12358e0000000p-8f, 0x1.1111120000000p-8f, 0x1.0fef020000000p-8f, 0x1.0ecf560000000p-8f, 0x1.0db20a0000000p-8f, 0x1.0c97140000000p-8f, 0x1.0b7e6e0000000p-8f, 0x1.0a68100000000p-8f, 0x1.0953f40000000p-8f, 0x1.0842100000000p-8f, 0x1.0732600000000p-8f, 0x1.0624de0000000p-8f, 0x1.0519800000000p-8f, 0x1.0410420000000p-8f, 0x1.03091c0000000p-8f, 0x1.0204080000000p-8f, 0x1.0101020000000p-8f, 0x1.0000000000000p-8f};
+// x / (float)w for an integer 1 <= w <= 256; rcp = shared-memory copy of c_rcpInt
+__device__ __forceinline__ float div_int(float x, int w, const float *rcp)
+{
+    const float c = (float)w;
+    const float ax = fabsf(x);
+    if (!(ax >= 0x1p-80f && ax < 0x1p11f))
+        return ax == 0.0f ? x : x / c; // +-0 / c = +-0 (black pixels, empty voxels); anything else out of the proven range: plain division
+    const float r = rcp[w];
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-q, c, x), r, q);
+}
+
 struct IntegrateParams
 {
     Mat4 M;        // world -> camera
@@ -425,7 +454,7 @@ struct IntegrateParams
 
 // returns true when the voxel changed
 __device__ __forceinline__ bool integrate_voxel(uint2 &raw, int gx, int gy, int gz, const IntegrateParams &P, const float *__restrict__ depth,
-                                                const uchar4 *__restrict__ rgb)
+                                                const uchar4 *__restrict__ rgb, const float *rcp /* shared copy of c_rcpInt */)
 {
     float mx = (float)gx * P.voxelSize, my = (float)gy * P.voxelSize, mz = (float)gz * P.voxelSize;
     float3 pc = mat4_mul_point(P.M, mx, my, mz, 1.0f);
@@ -444,11 +473,11 @@ __device__ __forceinline__ bool integrate_voxel(uint2 &raw, int gx, int gy, int 
 
     short sdf = (short)(raw.x & 0xffffu);
     int oldW = (int)((raw.x >> 16) & 0xffu);
-    float oldF = (float)sdf / 32767.0f;
+    float oldF = div_32767((float)sdf);
     float newF = fminf(1.0f, eta / P.mu);
     newF = (float)oldW * oldF + 1.0f * newF;
     int newW = oldW + 1;
-    newF /= (float)newW;
+    newF = div_int(newF, newW, rcp);
     newW = newW < P.maxW ? newW : P.maxW;
     unsigned usdf = (unsigned)(unsigned short)(short)(newF * 32767.0f);
     unsigned cr = (raw.x >> 24) & 0xffu, cg = raw.y & 0xffu, cb = (raw.y >> 8) & 0xffu, cw = (raw.y >> 16) & 0xffu;
@@ -464,15 +493,16 @@ __device__ __forceinline__ bool integrate_voxel(uint2 &raw, int gx, int gy, int 
         if (dy != 0) c = __ldg(&rgb[ix + (iy + 1) * P.W]);
         if (dx != 0 && dy != 0) d4 = __ldg(&rgb[(ix + 1) + (iy + 1) * P.W]);
         float ox = 1.0f - dx, oy = 1.0f - dy;
-        float mr = ((float)a.x * ox * oy + (float)b.x * dx * oy + (float)c.x * ox * dy + (float)d4.x * dx * dy) / 255.0f;
-        float mg = ((float)a.y * ox * oy + (float)b.y * dx * oy + (float)c.y * ox * dy + (float)d4.y * dx * dy) / 255.0f;
-        float mb = ((float)a.z * ox * oy + (float)b.z * dx * oy + (float)c.z * ox * dy + (float)d4.z * dx * dy) / 255.0f;
+        float mr = div_255((float)a.x * ox * oy + (float)b.x * dx * oy + (float)c.x * ox * dy + (float)d4.x * dx * dy);
+        float mg = div_255((float)a.y * ox * oy + (float)b.y * dx * oy + (float)c.y * ox * dy + (float)d4.y * dx * dy);
+        float mb = div_255((float)a.z * ox * oy + (float)b.z * dx * oy + (float)c.z * ox * dy + (float)d4.z * dx * dy);
         float ow = (float)cw;
-        float nr = ((float)cr / 255.0f) * ow + mr * 1.0f;
-        float ng = ((float)cg / 255.0f) * ow + mg * 1.0f;
-        float nb = ((float)cb / 255.0f) * ow + mb * 1.0f;
+        float nr = div_255((float)cr) * ow + mr * 1.0f;
+        float ng = div_255((float)cg) * ow + mg * 1.0f;
+        float nb = div_255((float)cb) * ow + mb * 1.0f;
         float nw = ow + 1.0f;
-        nr /= nw, ng /= nw, nb /= nw;
+        const int iw = (int)cw + 1; // nw as an integer, 1..256
+        nr = div_int(nr, iw, rcp), ng = div_int(ng, iw, rcp), nb = div_int(nb, iw, rcp);
         float cap = (float)(unsigned char)P.maxW;
         nw = nw < cap ? nw : cap;
         nr *= 255.0f, ng *= 255.0f, nb *= 255.0f;
@@ -504,9 +534,12 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
     // the two dependent global loads (visible id -> hash entry) are then off the single-thread TMA issue path
     __shared__ int dPtr[INT_DESC];
     __shared__ short4 dPos[INT_DESC];
+    __shared__ float sRcp[257];
 
     const int n = *nVis;
     const int tid = threadIdx.x;
+    for (int i = tid; i < 257; i += INT_THREADS)
+        sRcp[i] = c_rcpInt[i]; // visible to all threads after the first __syncthreads below
     if (tid == 0)
     {
         for (int s = 0; s < INT_STAGES; s++)
@@ -581,7 +614,7 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
                 int loc = tid + j * INT_THREADS;
                 int z = loc >> 6, y = (loc >> 3) & 7, x = loc & 7;
                 uint2 raw = buf[s][loc];
-                if (integrate_voxel(raw, gx0 + x, gy0 + y, gz0 + z, P, depth, rgb))
+                if (integrate_voxel(raw, gx0 + x, gy0 + y, gz0 + z, P, depth, rgb, sRcp))
                 {
                     buf[s][loc] = raw;
                     any = true;
@@ -627,9 +660,12 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_integrate_ws(Voxel *__restric
     __shared__ int sDirty[WS_STAGES];
     __shared__ int dPtr[WS_DESC];
     __shared__ short4 dPos[WS_DESC];
+    __shared__ float sRcp[257];
 
     const int n = *nVis;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 257; i += WS_THREADS)
+        sRcp[i] = c_rcpInt[i];
     if (tid == 0)
     {
         for (int s = 0; s < WS_STAGES; s++)
@@ -716,7 +752,7 @@ __global__ void __launch_bounds__(WS_THREADS, 4) k_integrate_ws(Voxel *__restric
                 const int loc = tid + j * (WS_CONSUMERS * 32);
                 const int z = loc >> 6, y = (loc >> 3) & 7, x = loc & 7;
                 uint2 raw = buf[s][loc];
-                if (integrate_voxel(raw, gx0 + x, gy0 + y, gz0 + z, P, depth, rgb))
+                if (integrate_voxel(raw, gx0 + x, gy0 + y, gz0 + z, P, depth, rgb, sRcp))
                 {
                     buf[s][loc] = raw;
                     any = true;
@@ -738,8 +774,12 @@ __global__ void __launch_bounds__(512) k_integrate_direct(Voxel *__restrict__ vb
                                                            const int *__restrict__ visIds, const int *__restrict__ nVis, IntegrateParams P,
                                                            const float *__restrict__ depth, const uchar4 *__restrict__ rgb)
 {
+    __shared__ float sRcp[257];
     const int n = *nVis;
     const int loc = threadIdx.x;
+    if (loc < 257)
+        sRcp[loc] = c_rcpInt[loc];
+    __syncthreads();
     const int z = loc >> 6, y = (loc >> 3) & 7, x = loc & 7;
     for (int i = blockIdx.x; i < n; i += gridDim.x)
     {
@@ -748,7 +788,7 @@ __global__ void __launch_bounds__(512) k_integrate_direct(Voxel *__restrict__ vb
             continue;
         uint2 *vp = reinterpret_cast<uint2 *>(vba + (size_t)e.ptr * SDF_BLOCK_SIZE3) + loc;
         uint2 raw = *vp;
-        if (integrate_voxel(raw, (int)e.px * SDF_BLOCK_SIZE + x, (int)e.py * SDF_BLOCK_SIZE + y, (int)e.pz * SDF_BLOCK_SIZE + z, P, depth, rgb))
+        if (integrate_voxel(raw, (int)e.px * SDF_BLOCK_SIZE + x, (int)e.py * SDF_BLOCK_SIZE + y, (int)e.pz * SDF_BLOCK_SIZE + z, P, depth, rgb, sRcp))
             *vp = raw;
     }
 }
