@@ -75,3 +75,15 @@ def test_itm_facade_driver_builds(engine_lib):
     from gps_slam_b200 import build
     exe = build.build_itm_driver()
     assert os.access(exe, os.X_OK)
+
+
+def test_abi_header_is_plain_c(tmp_path):
+    """include/gpsslam_b200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types in any signature) and as C++"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "gpsslam_b200.h"\nint main(void) { gsb_tsdf_config_t c; gsb_gs_config_t g; gsb_tsdf_default_config(&c); '
+                   'gsb_gs_default_config(&g); return c.width + g.width; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror"], ["g++", "-std=c++11", "-Wall", "-Werror", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
