@@ -157,9 +157,15 @@ void bwd_params_adam(const ParamPtrs &p, const ParamPtrs &m, const ParamPtrs &v,
                      int nUpper, const CamParams &cam, const SplatRec *recs, const SplatGrad *grads, float4 *aux /* [N*5] */,
                      const ParamPtrs *dbg, int *counters, cudaStream_t st);
 void reduce_loss(const float *lossTile, int T, double scale, double *out, cudaStream_t st);
-// removeRedundantGs + prunePoints: stable compaction of parameters (Adam state is re-created by the next cycle)
-void prune(const ParamPtrs &p, const ParamPtrs &tmp, int *nDev, int nUpper, float minOpac, float minScale, float maxScale, int *scanTmp,
-           int *counters, cudaStream_t st);
+// removeRedundantGs + prunePoints + removeFromOptimizer: stable compaction of the parameters and, for Gaussians that carry optimiser
+// state, of their Adam moments and state flag, into a second set of buffers (the caller swaps the sets afterwards)
+struct PruneBuffers
+{
+    ParamPtrs p, m, v, pOut, mOut, vOut;
+    const unsigned char *touched;
+    unsigned char *touchedOut;
+};
+void prune(const PruneBuffers &b, int *nDev, int nUpper, float minOpac, float minScale, float maxScale, int *scanTmp, int *counters, cudaStream_t st);
 
 // staged pieces with the argument layout of the reference's gsplat::*_tensor functions (C = 1)
 void staged_project_fwd(int N, const float *means, const float *quats, const float *scales, const CamParams &cam, int *radii, float *means2d,

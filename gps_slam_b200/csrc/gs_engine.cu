@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/gpsslam_b200.h"
@@ -24,8 +25,8 @@ struct gsb_gs
     int cap;         // Gaussian capacity
     int nUpper;      // host-side upper bound of the Gaussian count (exact after gsb_gs_count)
     int *nDev;       // device-side exact count
-    ParamPtrs p, tmp, m, v, dbg;
-    unsigned char *touched;
+    ParamPtrs p, tmp, m, v, mTmp, vTmp, dbg; // tmp / mTmp / vTmp: the other half of the prune's double buffers
+    unsigned char *touched, *touchedTmp;
     SplatRec *recs;
     SplatGrad *grads;
     float4 *aux;     // [cap*5] per-Gaussian SH basis / colour gradient / state flag between the two backward kernels
@@ -132,8 +133,11 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     rc |= alloc_params(e, e->tmp, e->cap);
     rc |= alloc_params(e, e->m, e->cap);
     rc |= alloc_params(e, e->v, e->cap);
+    rc |= alloc_params(e, e->mTmp, e->cap);
+    rc |= alloc_params(e, e->vTmp, e->cap);
     memset(&e->dbg, 0, sizeof e->dbg);
     rc |= dev_alloc(e, &e->touched, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->touchedTmp, (size_t)e->cap);
     rc |= dev_alloc(e, &e->recs, (size_t)e->cap);
     rc |= dev_alloc(e, &e->grads, (size_t)e->cap);
     rc |= dev_alloc(e, &e->aux, (size_t)e->cap * 5);
@@ -161,6 +165,7 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
         rc |= dev_alloc(e, &e->sb.flags, P);
         rc |= dev_alloc(e, &e->sb.chunkCnt, P / 1024 + 2);
         rc |= dev_alloc(e, &e->sb.pixOf, P);
+        rc |= dev_alloc(e, &e->sb.pixAll, P);
         rc |= dev_alloc(e, &e->sb.keys, (size_t)tbl);
         rc |= dev_alloc(e, &e->sb.heads, (size_t)tbl);
         rc |= dev_alloc(e, &e->sb.next, P);
@@ -249,6 +254,10 @@ extern "C" int gsb_gs_set_params(gsb_gs_t *e, int n, const float *means, const f
         return 1;
     e->hostInts[1] = n;
     GS_CUDA_OK(cudaMemcpyAsync(e->nDev, &e->hostInts[1], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    // a new model has no optimiser state
+    e->adamStep = 0;
+    if (n > 0)
+        GS_CUDA_OK(cudaMemsetAsync(e->touched, 0, (size_t)n, e->stream));
     GS_CUDA_OK(cudaStreamSynchronize(e->stream));
     e->nUpper = n;
     return 0;
@@ -407,16 +416,21 @@ extern "C" int gsb_gs_loss(gsb_gs_t *e, double *loss)
     return 0;
 }
 
-// SLAMPipeline::removeRedundantGs (slam/slam_pipeline.cpp:564-586) -> RawGaussianModel::prunePoints. No host round trip: the new
-// count stays on the device, the host keeps the old count as launch bound until the next gsb_gs_count.
+// SLAMPipeline::removeRedundantGs (slam/slam_pipeline.cpp:564-586) -> RawGaussianModel::prunePoints (+ removeFromOptimizer for every
+// optimiser, src/raw_gs_model.cpp:744-765: a surviving Gaussian keeps its own Adam moments).  No host round trip: the new count stays
+// on the device, the host keeps the old count as launch bound until the next gsb_gs_count.
 extern "C" int gsb_gs_prune(gsb_gs_t *e, float min_opac, float min_scale, float max_scale)
 {
     if (e->nUpper <= 0)
         return 0;
-    prune(e->p, e->tmp, e->nDev, e->nUpper, min_opac, min_scale, max_scale, e->scanTmp, e->bins.counters, e->stream);
-    ParamPtrs t = e->p;
-    e->p = e->tmp;
-    e->tmp = t;
+    PruneBuffers b;
+    b.p = e->p, b.m = e->m, b.v = e->v, b.pOut = e->tmp, b.mOut = e->mTmp, b.vOut = e->vTmp;
+    b.touched = e->touched, b.touchedOut = e->touchedTmp;
+    prune(b, e->nDev, e->nUpper, min_opac, min_scale, max_scale, e->scanTmp, e->bins.counters, e->stream);
+    std::swap(e->p, e->tmp);
+    std::swap(e->m, e->mTmp);
+    std::swap(e->v, e->vTmp);
+    std::swap(e->touched, e->touchedTmp);
     GS_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -778,25 +778,41 @@ __global__ void __launch_bounds__(1024) k_prune_scan(int *chunkCnt, int nChunks,
     }
 }
 
-__global__ void __launch_bounds__(1024) k_prune_scatter(ParamPtrs p, ParamPtrs q, const int *__restrict__ counters, float minOpac, float minScale,
+// copies one Gaussian's row of all six parameter arrays
+__device__ __forceinline__ void copy_param_row(const ParamPtrs &dst, int d, const ParamPtrs &src, int g)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        dst.means[d * 3 + i] = src.means[g * 3 + i], dst.scales[d * 3 + i] = src.scales[g * 3 + i], dst.dc[d * 3 + i] = src.dc[g * 3 + i];
+    reinterpret_cast<float4 *>(dst.quats)[d] = reinterpret_cast<const float4 *>(src.quats)[g];
+    dst.opac[d] = src.opac[g];
+    for (int e = 0; e < 45; e++)
+        dst.rest[(size_t)d * 45 + e] = src.rest[(size_t)g * 45 + e];
+}
+
+// Stable compaction of the survivors: parameters always; the Adam moments and the state flag travel with their Gaussian
+// (removeFromOptimizer, src/raw_gs_model.cpp:744-765) when it has optimiser state at all -- a Gaussian that has not been touched
+// since initOptimizers has m = v = 0 by definition and nothing to move.
+__global__ void __launch_bounds__(1024) k_prune_scatter(PruneBuffers b, const int *__restrict__ counters, float minOpac, float minScale,
                                                          float maxScale, const int *__restrict__ chunkOff)
 {
     __shared__ int ws[33];
     int g = blockIdx.x * 1024 + threadIdx.x;
     int nOld = counters[CNT_SCRATCH + 1];
-    int keep = (g < nOld) ? (int)prune_keep(p, g, minOpac, minScale, maxScale) : 0;
+    int keep = (g < nOld) ? (int)prune_keep(b.p, g, minOpac, minScale, maxScale) : 0;
     int total;
     int ex = block_excl_scan_1024(keep, ws, total);
     if (!keep)
         return;
     int d = chunkOff[blockIdx.x] + ex;
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        q.means[d * 3 + i] = p.means[g * 3 + i], q.scales[d * 3 + i] = p.scales[g * 3 + i], q.dc[d * 3 + i] = p.dc[g * 3 + i];
-    reinterpret_cast<float4 *>(q.quats)[d] = reinterpret_cast<const float4 *>(p.quats)[g];
-    q.opac[d] = p.opac[g];
-    for (int e = 0; e < 45; e++)
-        q.rest[(size_t)d * 45 + e] = p.rest[(size_t)g * 45 + e];
+    copy_param_row(b.pOut, d, b.p, g);
+    const unsigned char t = b.touched[g];
+    b.touchedOut[d] = t;
+    if (t)
+    {
+        copy_param_row(b.mOut, d, b.m, g);
+        copy_param_row(b.vOut, d, b.v, g);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -844,16 +860,15 @@ void reduce_loss(const float *lossTile, int T, double scale, double *out, cudaSt
     k_reduce_loss<<<1, 256, 0, st>>>(lossTile, T, scale, out);
 }
 
-void prune(const ParamPtrs &p, const ParamPtrs &tmp, int *nDev, int nUpper, float minOpac, float minScale, float maxScale, int *scanTmp,
-           int *counters, cudaStream_t st)
+void prune(const PruneBuffers &b, int *nDev, int nUpper, float minOpac, float minScale, float maxScale, int *scanTmp, int *counters, cudaStream_t st)
 {
     if (nUpper <= 0)
         return;
     int nChunks = cdiv(nUpper, 1024);
     GS_COUNT_LAUNCHES(3);
-    k_prune_count<<<nChunks, 1024, 0, st>>>(p, nDev, minOpac, minScale, maxScale, scanTmp);
+    k_prune_count<<<nChunks, 1024, 0, st>>>(b.p, nDev, minOpac, minScale, maxScale, scanTmp);
     k_prune_scan<<<1, 1024, 0, st>>>(scanTmp, nChunks, nDev, counters);
-    k_prune_scatter<<<nChunks, 1024, 0, st>>>(p, tmp, counters, minOpac, minScale, maxScale, scanTmp);
+    k_prune_scatter<<<nChunks, 1024, 0, st>>>(b, counters, minOpac, minScale, maxScale, scanTmp);
 }
 
 } // namespace gs

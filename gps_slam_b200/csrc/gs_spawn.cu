@@ -98,12 +98,15 @@ __global__ void __launch_bounds__(256) k_spawn_select(SpawnParams sp, const floa
     bool m = valid && (err > sp.colorErrorThres);
     if (haveGs)
         m = m && (renderAlpha[i] < sp.alphaMax);
-    // multi-GPU: the Gaussian set is sharded by spatial block (4 cm cells, the TSDF block size); each rank spawns its own
+    // multi-GPU: the Gaussian set is sharded by spatial block (4 cm cells, the TSDF block size); each rank spawns its own.  Pixels
+    // that another rank spawns are kept as flag 2: they are neighbours for the distCUDA2 scale of this rank's new Gaussians (the
+    // mask, the sampling and the ownership are pure functions of the pixel, so every rank sees the same full set).
+    bool mine = true;
     if (m && sp.world > 1)
     {
         int bx = (int)floorf(v.x * 25.0f), by = (int)floorf(v.y * 25.0f), bz = (int)floorf(v.z * 25.0f);
         unsigned hsh = ((unsigned)bx * 73856093u) ^ ((unsigned)by * 19349669u) ^ ((unsigned)bz * 83492791u);
-        m = (int)(hash_u32(hsh) % (unsigned)sp.world) == sp.rank;
+        mine = (int)(hash_u32(hsh) % (unsigned)sp.world) == sp.rank;
     }
     // addGaussians keeps a uniformly random subset of the masked pixels (randperm prefix of length ratio * M); here every masked
     // pixel is kept independently with probability ratio (counter-based hash of pixel and seed): same inclusion probability,
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(256) k_spawn_select(SpawnParams sp, const floa
         unsigned h = hash_u32((unsigned)i ^ hash_u32(sp.seed));
         m = h < sp.ratioThreshold;
     }
-    flags[i] = m ? 1 : 0;
+    flags[i] = m ? (mine ? 1 : 2) : 0;
 }
 
 // stable compaction of the flagged pixels (two-level scan, 1024 pixels per chunk)
@@ -152,18 +155,22 @@ __device__ __forceinline__ int block_excl_scan_1024s(int v, int *ws, int &total)
     return r;
 }
 
-__global__ void __launch_bounds__(1024) k_spawn_count(int P, const unsigned char *__restrict__ flags, int *chunkCnt)
+// anyOwner = 0: the pixels this rank spawns (flag 1); 1: the pixels any rank spawns (flag 1 or 2)
+__device__ __forceinline__ int flag_selected(unsigned char f, int anyOwner) { return anyOwner ? (f != 0) : (f == 1); }
+
+__global__ void __launch_bounds__(1024) k_spawn_count(int P, const unsigned char *__restrict__ flags, int anyOwner, int *chunkCnt)
 {
     __shared__ int ws[33];
     int i = blockIdx.x * 1024 + threadIdx.x;
-    int f = i < P ? flags[i] : 0;
+    int f = i < P ? flag_selected(flags[i], anyOwner) : 0;
     int total;
     block_excl_scan_1024s(f, ws, total);
     if (threadIdx.x == 0)
         chunkCnt[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) k_spawn_scan(int *chunkCnt, int nChunks, const int *nDev, int cap, int *counters)
+// slot: counters[CNT_SCRATCH] (number of new Gaussians, limited by the room left) or counters[CNT_SCRATCH + 1] (size of the KNN point set)
+__global__ void __launch_bounds__(1024) k_spawn_scan(int *chunkCnt, int nChunks, const int *nDev, int cap, int *counters, int slot)
 {
     __shared__ int ws[33];
     __shared__ int carry;
@@ -185,29 +192,32 @@ __global__ void __launch_bounds__(1024) k_spawn_scan(int *chunkCnt, int nChunks,
     }
     if (threadIdx.x == 0)
     {
-        int room = cap - *nDev;
         int m = carry;
-        if (m > room)
+        if (slot == CNT_SCRATCH)
         {
-            m = room < 0 ? 0 : room;
-            atomicOr(&counters[CNT_OVERFLOW], 4);
+            int room = cap - *nDev;
+            if (m > room)
+            {
+                m = room < 0 ? 0 : room;
+                atomicOr(&counters[CNT_OVERFLOW], 4);
+            }
         }
-        counters[CNT_SCRATCH] = m; // number of new Gaussians
+        counters[slot] = m;
     }
 }
 
-__global__ void __launch_bounds__(1024) k_spawn_compact(int P, const unsigned char *__restrict__ flags, const int *__restrict__ chunkOff,
-                                                         const int *__restrict__ counters, int *pixOf)
+__global__ void __launch_bounds__(1024) k_spawn_compact(int P, const unsigned char *__restrict__ flags, int anyOwner, const int *__restrict__ chunkOff,
+                                                         const int *__restrict__ counters, int slot, int *pixOf)
 {
     __shared__ int ws[33];
     int i = blockIdx.x * 1024 + threadIdx.x;
-    int f = i < P ? flags[i] : 0;
+    int f = i < P ? flag_selected(flags[i], anyOwner) : 0;
     int total;
     int ex = block_excl_scan_1024s(f, ws, total);
     if (f)
     {
         int d = chunkOff[blockIdx.x] + ex;
-        if (d < counters[CNT_SCRATCH])
+        if (d < counters[slot])
             pixOf[d] = i;
     }
 }
@@ -228,12 +238,12 @@ __device__ __forceinline__ unsigned cell_hash(unsigned long long k)
 }
 constexpr unsigned long long KEY_EMPTY = 0xffffffffffffffffULL;
 
-__global__ void __launch_bounds__(256) k_knn_build(const int *__restrict__ counters, const int *__restrict__ pixOf,
+__global__ void __launch_bounds__(256) k_knn_build(const int *__restrict__ counters, int countSlot, const int *__restrict__ pixOf,
                                                     const float4 *__restrict__ vertex4, float voxelSize, float invCell, unsigned long long *keys,
                                                     int *heads, int *next, unsigned mask)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= counters[CNT_SCRATCH])
+    if (i >= counters[countSlot])
         return;
     float3 v = world_vertex(vertex4, pixOf[i], voxelSize);
     unsigned long long key = cell_key((int)floorf(v.x * invCell), (int)floorf(v.y * invCell), (int)floorf(v.z * invCell));
@@ -250,8 +260,10 @@ __global__ void __launch_bounds__(256) k_knn_build(const int *__restrict__ count
     }
 }
 
+// pixOf: the pixels this rank spawns; pixKnn: the point set of the KNN grid (the same list on one GPU, every rank's pixels otherwise)
 __global__ void __launch_bounds__(128) k_spawn_write(SpawnParams sp, const int *__restrict__ counters, const int *__restrict__ pixOf,
-                                                      const float4 *__restrict__ vertex4, const float *__restrict__ gt, float invCell,
+                                                      const int *__restrict__ pixKnn, const float4 *__restrict__ vertex4,
+                                                      const float *__restrict__ gt, float invCell,
                                                       const unsigned long long *__restrict__ keys, const int *__restrict__ heads,
                                                       const int *__restrict__ next, unsigned mask, ParamPtrs p, const int *__restrict__ nDev,
                                                       unsigned char *touched)
@@ -287,9 +299,10 @@ __global__ void __launch_bounds__(128) k_spawn_write(SpawnParams sp, const int *
                 }
                 for (int j = head; j >= 0; j = next[j])
                 {
-                    if (j == i)
+                    const int pj = pixKnn[j];
+                    if (pj == pix)
                         continue;
-                    float3 u = world_vertex(vertex4, pixOf[j], sp.voxelSize);
+                    float3 u = world_vertex(vertex4, pj, sp.voxelSize);
                     float ex = u.x - v.x, ey = u.y - v.y, ez = u.z - v.z;
                     float dist = ex * ex + ey * ey + ez * ez;
 #pragma unroll
@@ -384,13 +397,26 @@ void spawn(const SpawnParams &sp, const SpawnBuffers &b, const float4 *vertex4, 
     const float invCell = 1.0f / cell;
     GS_COUNT_LAUNCHES(7);
     k_spawn_select<<<cdiv(P, 256), 256, 0, st>>>(sp, vertex4, depthMap, colorMap, gt, renderRgb, renderAlpha, nDev, b.flags);
-    k_spawn_count<<<nChunks, 1024, 0, st>>>(P, b.flags, b.chunkCnt);
-    k_spawn_scan<<<1, 1024, 0, st>>>(b.chunkCnt, nChunks, nDev, cap, counters);
-    k_spawn_compact<<<nChunks, 1024, 0, st>>>(P, b.flags, b.chunkCnt, counters, b.pixOf);
+    k_spawn_count<<<nChunks, 1024, 0, st>>>(P, b.flags, 0, b.chunkCnt);
+    k_spawn_scan<<<1, 1024, 0, st>>>(b.chunkCnt, nChunks, nDev, cap, counters, CNT_SCRATCH);
+    k_spawn_compact<<<nChunks, 1024, 0, st>>>(P, b.flags, 0, b.chunkCnt, counters, CNT_SCRATCH, b.pixOf);
+    // the KNN point set: this rank's new points on one GPU, every rank's otherwise (so that a new Gaussian next to a block border
+    // gets the scale it would get on one GPU)
+    const int *pixKnn = b.pixOf;
+    int knnSlot = CNT_SCRATCH;
+    if (sp.world > 1)
+    {
+        GS_COUNT_LAUNCHES(3);
+        k_spawn_count<<<nChunks, 1024, 0, st>>>(P, b.flags, 1, b.chunkCnt);
+        k_spawn_scan<<<1, 1024, 0, st>>>(b.chunkCnt, nChunks, nDev, cap, counters, CNT_SCRATCH + 1);
+        k_spawn_compact<<<nChunks, 1024, 0, st>>>(P, b.flags, 1, b.chunkCnt, counters, CNT_SCRATCH + 1, b.pixAll);
+        pixKnn = b.pixAll, knnSlot = CNT_SCRATCH + 1;
+    }
     cudaMemsetAsync(b.keys, 0xff, sizeof(unsigned long long) * ((size_t)b.tableMask + 1), st);
     cudaMemsetAsync(b.heads, 0xff, sizeof(int) * ((size_t)b.tableMask + 1), st);
-    k_knn_build<<<cdiv(P, 256), 256, 0, st>>>(counters, b.pixOf, vertex4, sp.voxelSize, invCell, b.keys, b.heads, b.next, b.tableMask);
-    k_spawn_write<<<cdiv(P, 128), 128, 0, st>>>(sp, counters, b.pixOf, vertex4, gt, invCell, b.keys, b.heads, b.next, b.tableMask, p, nDev, touched);
+    k_knn_build<<<cdiv(P, 256), 256, 0, st>>>(counters, knnSlot, pixKnn, vertex4, sp.voxelSize, invCell, b.keys, b.heads, b.next, b.tableMask);
+    k_spawn_write<<<cdiv(P, 128), 128, 0, st>>>(sp, counters, b.pixOf, pixKnn, vertex4, gt, invCell, b.keys, b.heads, b.next, b.tableMask, p, nDev,
+                                                touched);
     k_spawn_commit<<<1, 1, 0, st>>>(nDev, counters);
 }
 

@@ -24,6 +24,7 @@ struct SpawnBuffers
     unsigned char *flags; // [P]
     int *chunkCnt;        // [ceil(P/1024)]
     int *pixOf;           // [P] pixel of each new Gaussian
+    int *pixAll;          // [P] multi-GPU: pixel of each new Gaussian of ANY rank (the KNN point set)
     unsigned long long *keys; // [tableMask+1]
     int *heads;           // [tableMask+1]
     int *next;            // [P]

@@ -21,6 +21,7 @@
 #include <new>
 
 #include "icp.h"
+#include "spd_solve.h"
 
 namespace icp
 {
@@ -311,81 +312,6 @@ __device__ __forceinline__ void grid_sync(unsigned *bar, unsigned nblocks)
     __syncthreads();
 }
 
-// ORUtils::Cholesky (ORUtils/Cholesky.h:18-86) restated: factorisation + Backsub
-__device__ __host__ inline void cholesky_solve(const float *mat, int size, const float *v, float *result)
-{
-    float ch[36], yv[6];
-    for (int i = 0; i < size * size; i++)
-        ch[i] = mat[i];
-    for (int c = 0; c < size; c++)
-    {
-        float inv_diag = 1;
-        for (int r = c; r < size; r++)
-        {
-            float val = ch[c + r * size];
-            for (int c2 = 0; c2 < c; c2++)
-                val -= ch[c + c2 * size] * ch[c2 + r * size];
-            if (r == c)
-            {
-                ch[c + r * size] = val;
-                inv_diag = 1.0f / val;
-            }
-            else
-            {
-                ch[r + c * size] = val;
-                ch[c + r * size] = val * inv_diag;
-            }
-        }
-    }
-    for (int i = 0; i < size; i++)
-    {
-        float val = v[i];
-        for (int j = 0; j < i; j++)
-            val -= ch[j + i * size] * yv[j];
-        yv[i] = val;
-    }
-    for (int i = 0; i < size; i++)
-        yv[i] /= ch[i + i * size];
-    for (int i = size - 1; i >= 0; i--)
-    {
-        float val = yv[i];
-        for (int j = i + 1; j < size; j++)
-            val -= ch[i + j * size] * result[j];
-        result[i] = val;
-    }
-}
-
-inline float cholesky_det(const float *mat, int size)
-{
-    float ch[36];
-    for (int i = 0; i < size * size; i++)
-        ch[i] = mat[i];
-    for (int c = 0; c < size; c++)
-    {
-        float inv_diag = 1;
-        for (int r = c; r < size; r++)
-        {
-            float val = ch[c + r * size];
-            for (int c2 = 0; c2 < c; c2++)
-                val -= ch[c + c2 * size] * ch[c2 + r * size];
-            if (r == c)
-            {
-                ch[c + r * size] = val;
-                inv_diag = 1.0f / val;
-            }
-            else
-            {
-                ch[r + c * size] = val;
-                ch[c + r * size] = val * inv_diag;
-            }
-        }
-    }
-    float ret = 1.0f;
-    for (int i = 0; i < size; ++i)
-        ret *= ch[i + i * size];
-    return ret * ret;
-}
-
 // expand the 21 lower-triangular sums into the reference's 6x6 layout hessian[r + c*6] (ITMExtendedTracker_CUDA.cu:186-190)
 __device__ __host__ inline void expand_hessian(const float *acc, int noPara, float *H, float *g)
 {
@@ -476,10 +402,10 @@ __device__ void lm_step(State &S, const float *sum, int type, float terminationT
         for (int r = 0; r < 3; r++)
             for (int c = 0; c < 3; c++)
                 small[r + c * 3] = A[r + c * 6];
-        cholesky_solve(small, 3, S.nabla_good, step);
+        SpdFactor<3>(small).solve(S.nabla_good, step);
     }
     else
-        cholesky_solve(A, 6, S.nabla_good, step);
+        SpdFactor<6>(A).solve(S.nabla_good, step);
     // ApplyDelta
     float st[6];
     if (type == IT_ROTATION)
@@ -843,12 +769,12 @@ static void update_pose_quality(Tracker *t, const State &S, float thresh0)
         float h[36];
         for (int i = 0; i < 36; i++)
             h[i] = S.hessian_q[i] * nf1;
-        d1 = cholesky_det(h, 6);
+        d1 = SpdFactor<6>(h).det_squared();
         if (std::isnan(d1))
             d1 = 0.f;
         for (int i = 0; i < 36; i++)
             h[i] = S.hessian_q[i] * nf2;
-        d2 = cholesky_det(h, 6);
+        d2 = SpdFactor<6>(h).det_squared();
         if (std::isnan(d2))
             d2 = 0.f;
     }

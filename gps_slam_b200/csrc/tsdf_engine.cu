@@ -51,6 +51,8 @@ struct gsb_tsdf
     int agePointCloud;         // ITMTrackingState::age_pointCloud (-1 = no valid point cloud yet)
     bool haveFrame;
     const void *lastRgba;      // RGBA frame consumed by the last ProcessFrame (own upload buffer or the caller's resident frame)
+    bool stageTiming;          // gsb_tsdf_enable_stage_timing: CUDA events between the stages of ProcessFrame
+    cudaEvent_t stageEv[7];
     std::vector<void *> allocs;
 };
 
@@ -97,6 +99,11 @@ extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
         e->cfg.num_blocks = SDF_DEFAULT_BLOCK_NUM;
     if (e->cfg.max_w <= 0)
         e->cfg.max_w = 100;
+    if (e->cfg.max_w > 255)
+    {
+        delete e;
+        return gs_set_error(__FILE__, __LINE__, "max_w > 255: the voxel's depth weight is one byte (ITMVoxel_s_rgb::w_depth)");
+    }
     const int W = cfg->width, H = cfg->height, P = W * H;
     tsdf::Scene &s = e->scene;
     s.E = SDF_TOTAL_ENTRIES;
@@ -132,6 +139,7 @@ extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
     e->frame.depth_mm = e->depth_mm, e->frame.rgba = e->rgba, e->frame.depth_f = e->depth_f, e->frame.W = W, e->frame.H = H;
     e->cam.fx = cfg->fx, e->cam.fy = cfg->fy, e->cam.cx = cfg->cx, e->cam.cy = cfg->cy;
     e->tracker = nullptr;
+    e->stageTiming = false;
     e->trackingActive = cfg->tracker != 0;
     if (cfg->tracker != 0)
     {
@@ -153,6 +161,9 @@ extern "C" void gsb_tsdf_destroy(gsb_tsdf_t *e)
     cudaStreamSynchronize(e->stream);
     if (e->tracker)
         icp::destroy_tracker(e->tracker);
+    if (e->stageTiming)
+        for (cudaEvent_t ev : e->stageEv)
+            cudaEventDestroy(ev);
     for (void *p : e->allocs)
         cudaFree(p);
     cudaStreamDestroy(e->ownStream);
@@ -239,6 +250,12 @@ static void refresh_camera(gsb_tsdf *e)
 static int process_resident(gsb_tsdf *e, const float *gt_c2w)
 {
     cudaStream_t st = e->stream;
+    auto mark = [&](int i)
+    {
+        if (e->stageTiming)
+            cudaEventRecord(e->stageEv[i], st);
+    };
+    mark(0);
     // --- tracking (ITMBasicEngine.tpp:273-280)
     if (!e->trackingActive)
     {
@@ -268,15 +285,21 @@ static int process_resident(gsb_tsdf *e, const float *gt_c2w)
         }
     }
     refresh_camera(e);
+    mark(1);
     // --- fusion (ITMDenseMapper::ProcessFrame)
     tsdf::allocate(e->scene, e->frame, e->cam, st);
+    mark(2);
     tsdf::integrate(e->scene, e->frame, e->cam, e->cfg.integrate_variant, st);
+    mark(3);
     e->framesProcessed++;
     // --- ITMTrackingController::Prepare (always: requiresPointCloudRendering() is constant true)
     const int W = e->cfg.width, H = e->cfg.height;
     tsdf::expected_depth_live(e->scene, e->cam, W, H, e->minmaxLive, st);
+    mark(4);
     tsdf::raycast(e->scene, e->cam, W, H, e->minmaxLive, e->rayLive, nullptr, true, st);
+    mark(5);
     tsdf::icp_maps(e->scene, e->cam, W, H, e->rayLive, e->pointsMap, e->normalsMap, st);
+    mark(6);
     e->pose_pointCloud = e->pose_d;
     e->agePointCloud = (e->agePointCloud == -1) ? -2 : 0;
     e->haveFrame = true;
@@ -409,6 +432,31 @@ extern "C" int gsb_tsdf_read(gsb_tsdf_t *e, int what, void *dst, size_t bytes)
         return gs_set_error(__FILE__, __LINE__, "read larger than the buffer");
     E_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream));
     E_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// Measurement aid: CUDA events between the stages of ProcessFrame (track | allocate | integrate | expected depth | raycast | ICP maps)
+extern "C" int gsb_tsdf_enable_stage_timing(gsb_tsdf_t *e, int on)
+{
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    if (on && !e->stageTiming)
+        for (cudaEvent_t &ev : e->stageEv)
+            E_CUDA(cudaEventCreate(&ev));
+    if (!on && e->stageTiming)
+        for (cudaEvent_t ev : e->stageEv)
+            cudaEventDestroy(ev);
+    e->stageTiming = on != 0;
+    return 0;
+}
+// device times (ms) of the six stages of the last ProcessFrame; synchronises the stream
+extern "C" int gsb_tsdf_stage_times(gsb_tsdf_t *e, float *ms6)
+{
+    if (!e || !ms6 || !e->stageTiming || !e->haveFrame)
+        return gs_set_error(__FILE__, __LINE__, "stage timing is not enabled or no frame was processed");
+    E_CUDA(cudaEventSynchronize(e->stageEv[6]));
+    for (int i = 0; i < 6; i++)
+        E_CUDA(cudaEventElapsedTime(&ms6[i], e->stageEv[i], e->stageEv[i + 1]));
     return 0;
 }
 

@@ -379,12 +379,17 @@ template <class TVoxel, class TIndex> class ITMBasicEngine : public ITMMainEngin
         f.write((const char *)&count, sizeof(size_t));
         f.write((const char *)data, (std::streamsize)(count * elemSize));
     }
-    static size_t readBlock(const std::string &path, std::vector<char> &data, size_t elemSize)
+    // expectedCount: the element count this engine's arrays have; a header that says otherwise (truncated / foreign / corrupt file)
+    // is rejected before anything is allocated from it
+    static size_t readBlock(const std::string &path, std::vector<char> &data, size_t elemSize, size_t expectedCount)
     {
         std::ifstream f(path, std::ios::binary);
         if (!f) DIEWITHEXCEPTION("could not open " + path + " for reading");
         size_t count = 0;
         f.read((char *)&count, sizeof(size_t));
+        if ((size_t)f.gcount() != sizeof(size_t)) DIEWITHEXCEPTION(path + " has no header");
+        if (count != expectedCount)
+            DIEWITHEXCEPTION(path + " holds " + std::to_string(count) + " elements, this engine expects " + std::to_string(expectedCount));
         data.resize(count * elemSize);
         f.read(data.data(), (std::streamsize)data.size());
         if ((size_t)f.gcount() != data.size()) DIEWITHEXCEPTION(path + " is shorter than its header says");
@@ -520,17 +525,21 @@ public:
     {
         const std::string scene = saveInputDirectory + "/Scene";
         std::vector<char> hash, voxels, list;
-        const size_t nHash = readBlock(scene + "/hash.dat", hash, 16), nVox = readBlock(scene + "/voxel.dat", voxels, 8);
-        for (const char *name : {"/alloc.dat", "/excess.dat"})
+        const size_t blocks = (size_t)(cfg_.num_blocks > 0 ? cfg_.num_blocks : 0x40000);
+        const size_t nHash = readBlock(scene + "/hash.dat", hash, 16, kHashEntries), nVox = readBlock(scene + "/voxel.dat", voxels, 8, blocks * 512);
+        for (int which = 0; which < 2; which++)
         {
-            const size_t n = readBlock(scene + name, list, 4);
+            const size_t n = readBlock(scene + (which ? "/excess.dat" : "/alloc.dat"), list, 4, which ? kExcess : blocks);
             for (size_t i = 0; i < n; i++)
                 if (((const int *)list.data())[i] != (int)i)
                     DIEWITHEXCEPTION("gps_slam_b200: free lists are not the identity permutation (scene saved with swapping): not supported");
         }
         int lastBlock = 0, lastExcess = 0;
-        std::ifstream(scene + "/vba.txt") >> lastBlock;
-        std::ifstream(scene + "/last.txt") >> lastExcess;
+        {
+            std::ifstream fv(scene + "/vba.txt"), fl(scene + "/last.txt");
+            if (!(fv >> lastBlock)) DIEWITHEXCEPTION("could not read " + scene + "/vba.txt");
+            if (!(fl >> lastExcess)) DIEWITHEXCEPTION("could not read " + scene + "/last.txt");
+        }
         check(gsb_tsdf_load_scene(h_, hash.data(), nHash, voxels.data(), nVox, lastBlock, lastExcess), "gsb_tsdf_load_scene");
     }
     void SaveToFile() {}

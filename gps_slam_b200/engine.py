@@ -93,6 +93,8 @@ def load_library():
     L.gsb_tsdf_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.gsb_tsdf_counter.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     L.gsb_tsdf_run_stage.argtypes = [C.c_void_p, C.c_int]
+    L.gsb_tsdf_enable_stage_timing.argtypes = [C.c_void_p, C.c_int]
+    L.gsb_tsdf_stage_times.argtypes = [C.c_void_p, C.c_void_p]
     L.gsb_tsdf_icp_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
     L.gsb_tsdf_set_tracking_frames.argtypes = [C.c_void_p, C.c_int]
     L.gsb_tsdf_tracker_result.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -267,6 +269,15 @@ class TsdfEngine:
 
     def run_stage(self, stage):
         _check(self.L.gsb_tsdf_run_stage(self.h_, stage))
+
+    def enable_stage_timing(self, on=True):
+        _check(self.L.gsb_tsdf_enable_stage_timing(self.h_, 1 if on else 0))
+
+    def stage_times(self):
+        """device ms of track | allocate | integrate | expected depth | raycast | ICP maps of the last ProcessFrame (synchronises)"""
+        ms = (C.c_float * 6)()
+        _check(self.L.gsb_tsdf_stage_times(self.h_, ms))
+        return [float(x) for x in ms]
 
     def counter(self, which):
         v = C.c_int(0)

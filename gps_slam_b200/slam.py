@@ -319,22 +319,31 @@ class SlamPipeline:
             cam = cams[ci]
             if self.world > 1:
                 self.gs.forward_partial(cam.c2w_slam, self.intr, cam.depth_map, self.acc5, True)
-                parallel.allreduce_sum_(self.acc5)      # the one collective of an iteration: [H,W,5] fp32 partial image
+                self._allreduce_acc5()                  # the one collective of an iteration: [H,W,5] fp32 partial image
                 self.gs.train_finish(cam.depth_map, cam.color_map, cam.image, self.acc5)
             else:
                 self.gs.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image)
+
+    def _allreduce_acc5(self):
+        """sum of the per-rank partial images, enqueued on the Gaussian stream sG -- the stream forward_partial wrote acc5 on and
+        train_finish / render_finish read it on -- whatever torch's current stream is in the caller"""
+        with torch.cuda.stream(self.sG):
+            parallel.allreduce_sum_(self.acc5)
 
     def _forward_all(self, cam, rgb, depth, alpha):
         """gesForward over the Gaussians of every rank"""
         if self.world > 1:
             self.gs.forward_partial(cam.c2w_slam, self.intr, cam.depth_map, self.acc5, False)
-            parallel.allreduce_sum_(self.acc5)
+            self._allreduce_acc5()
             self.gs.render_finish(cam.depth_map, cam.color_map, self.acc5, rgb, depth, alpha)
         else:
             self.gs.forward(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, rgb, depth, alpha)
 
     def _remove_redundant(self):
         c = self.cfg
+        # the next cycle re-creates the optimisers (localOptimize -> initOptimizers) before anything reads their state, so drop the
+        # state now: the prune then has no Adam moments to carry along (gsb_gs_prune keeps them otherwise, like removeFromOptimizer)
+        self.gs.initOptimizers()
         self.gs.prunePoints(c["low_opac_thres"], c["small_scale_thres"], c["large_scale_thres"])
 
     # ------------------------------------------------------------------------------------------------------------
@@ -379,7 +388,7 @@ class SlamPipeline:
 
     def scaling(self):
         # the frame sequence is fixed; with N GPUs the same Gaussians and the same frames are split N ways
-        return "weak" if self.world == 1 else "strong"
+        return "strong"
 
     def _time(self, stream, fn, reps, flush):
         ms = []

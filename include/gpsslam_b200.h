@@ -48,7 +48,7 @@ typedef struct gsb_tsdf_config
     float mu;                     /* ITMSceneParams::mu  (trunc_dist)                                        */
     float view_frustum_min;       /* ITMSceneParams::viewFrustum_min                                          */
     float view_frustum_max;       /* ITMSceneParams::viewFrustum_max                                          */
-    int max_w;                    /* ITMSceneParams::maxW, reference default 100 (ITMLibSettings.cpp:10)      */
+    int max_w;                    /* ITMSceneParams::maxW, reference default 100 (ITMLibSettings.cpp:10); 1..255 (one byte per voxel) */
     int num_blocks;               /* SDF_LOCAL_BLOCK_NUM, reference 0x40000; 0 = default                      */
     int tracker;                  /* 0 = ground-truth poses (turnOffTracking), 1 = extended, 2 = icp           */
     int device;                   /* CUDA device ordinal                                                       */
@@ -124,6 +124,11 @@ int gsb_tsdf_load_scene(gsb_tsdf_t *e, const void *hash_entries_host, size_t n_e
 /* Single stages on the current frame / pose, for profiling and stage-level parity.
  * stage: 0 allocate (B1-B4), 1 integrate (B5), 2 expected depth (B6), 3 raycast (B7), 4 ICP maps (B8) */
 int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage);
+/* Measurement aid (bench.py roofline): CUDA events between the stages of ProcessFrame, so that each stage's device time is read
+ * from fresh frames inside the loop.  ms6 = track | allocate | integrate | expected depth | raycast | ICP maps of the last frame;
+ * gsb_tsdf_stage_times synchronises the engine's stream. */
+int gsb_tsdf_enable_stage_timing(gsb_tsdf_t *e, int on);
+int gsb_tsdf_stage_times(gsb_tsdf_t *e, float *ms6);
 
 /* ===================================================================================================
  * C.  ICP tracker  -- replaces ITMExtendedTracker (tracker == 1, the reference's compiled-in default) and ITMDepthTracker
@@ -192,7 +197,9 @@ int gsb_gs_render(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, f
 int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
                       const float *base_color_dev, const float *gt_rgb_dev);
 int gsb_gs_loss(gsb_gs_t *e, double *loss);                               /* loss["total"] of the last step; synchronises */
-/* SLAMPipeline::removeRedundantGs + prunePoints (remove_configs.low_opac_thres, small_scale_thres, large_scale_thres) */
+/* SLAMPipeline::removeRedundantGs + prunePoints (remove_configs.low_opac_thres, small_scale_thres, large_scale_thres).
+ * Like the reference's removeFromOptimizer (src/raw_gs_model.cpp:744-765) the surviving Gaussians keep their Adam moments, so
+ * gsb_gs_train_step may follow directly; gsb_gs_init_optimizers before the prune makes it cheaper (no state to move). */
 int gsb_gs_prune(gsb_gs_t *e, float min_opac, float min_scale, float max_scale);
 
 /* SLAMPipeline::initNewGaussians + SLAMGaussianModel::addGaussians (slam/slam_pipeline.cpp:450-526, slam/slam_gs_model.cpp:5-56) */

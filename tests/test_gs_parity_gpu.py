@@ -155,3 +155,54 @@ def test_sharded_partial_finish_matches_single_engine(engine_lib):
         single.close()
         for e in shards:
             e.close()
+
+
+def test_prune_keeps_adam_state_of_survivors(engine_lib):
+    """train, prune, train again WITHOUT initOptimizers in between: every surviving Gaussian must continue with its own Adam moments
+    (removeFromOptimizer, src/raw_gs_model.cpp:744-765).  The moments are tracked on the host with the oracle's Adam from the
+    engine's dumped parameter gradients, compacted with the same keep mask, and must predict the engine's third step."""
+    from gps_slam_b200.engine import GaussianEngine
+    from oracle import gs_oracle as go
+    W, H, N = 320, 192, 3000
+    p = random_splats(N, seed=41)
+    c2w, K = camera(W, H, 41)
+    intr = gc.intr_of(K, W, H)
+    ref_depth, base, gt = scene_images(W, H, 41)
+    dev = torch.device("cuda", 0)
+    rd, bs, g = [torch.from_numpy(a).to(dev) for a in (ref_depth, base, gt)]
+    keys = ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities")
+    eng = GaussianEngine(W, H, capacity=N)
+    try:
+        eng.set_params(p)
+        eng.enable_grad_dump(True)
+        eng.initOptimizers()
+        m = {k: np.zeros((N, np.asarray(p[k], np.float32).reshape(N, -1).shape[1]), np.float32) for k in keys}
+        v = {k: np.zeros_like(m[k]) for k in keys}
+        for step in (1, 2):
+            eng.train_step(c2w, intr, rd, bs, g)
+            pg = eng.param_grads(N)
+            for k in keys:
+                scratch = np.zeros_like(m[k])
+                go.adam_step(scratch, pg[k].reshape(N, -1), m[k], v[k], step, gc.LR[k])
+        cur = eng.get_params()
+        s = np.exp(cur["scales"]).max(1)
+        o = 1.0 / (1.0 + np.exp(-cur["opacities"].reshape(-1)))
+        min_opac, min_scale, max_scale = 0.35, 0.004, 0.027
+        keep = ~((s < min_scale) | (s > max_scale) | (o < min_opac))
+        eng.prunePoints(min_opac, min_scale, max_scale)
+        n2 = eng.getGaussianNum()
+        assert n2 == int(keep.sum()) and 0.3 * N < n2 < 0.9 * N, (n2, int(keep.sum()))
+        eng.train_step(c2w, intr, rd, bs, g)          # step 3 of the same optimisers
+        pg = eng.param_grads(n2)
+        after = eng.get_params()
+        moved = 0
+        for k in keys:
+            exp = np.array(cur[k], np.float32, copy=True).reshape(N, -1)[keep]
+            mk, vk = m[k][keep].copy(), v[k][keep].copy()
+            go.adam_step(exp, pg[k].reshape(n2, -1), mk, vk, 3, gc.LR[k])
+            got = after[k].reshape(n2, -1)
+            gc.close_frac("adam after prune " + k, got, exp, 1e-6, 1e-4)
+            moved += int((got != np.asarray(cur[k], np.float32).reshape(N, -1)[keep]).sum())
+        assert moved > 0
+    finally:
+        eng.close()
