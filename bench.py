@@ -29,14 +29,27 @@ if ROOT not in sys.path:
 FRAMES_PER_STEP = 10  # local_opt_interval (office0.yaml:52)
 
 
+# BASELINE.json `configs` by index (0 is the CPU-engine plumbing case = --impl reference):
+#   name, camera, frames of the whole sequence, tracker (0 = ground-truth poses), what it is
+CONFIGS = {
+    2: dict(name="Replica office0 work_mode=train, use_gt_pose=true", camera="replica", frames=2000, track=0),
+    3: dict(name="Replica room0 work_mode=train, online ICP tracking (use_gt_pose=false, extended tracker)", camera="replica", frames=2000, track=1),
+    4: dict(name="GPS_SLAM Indoor activity_room shape (Azure Kinect 1280x720) work_mode=train, use_gt_pose=true", camera="kinect", frames=2680, track=0),
+    5: dict(name="synthetic 1M-Gaussian stress scene at 1920x1080, rasteriser-backward HBM-roofline sweep", camera=None, frames=0, track=0),
+}
+TAIL_FRAMES = 50   # frames of the sequence left after the timed window (the window of the default driver run is frames 1750-1950 of 2000)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs index (default 2: the config the metric is quoted on)")
+    ap.add_argument("--frames", type=int, default=0, help="length of the whole sequence (0 = the config's: 2000 / 2680); the timed window sits near its end")
     ap.add_argument("--mode", default=None, choices=["train", "recon"])
-    ap.add_argument("--track", type=int, default=0, help="0: ground-truth poses (use_gt_pose=true, office0 config); 1: extended ICP tracker; 2: icp")
+    ap.add_argument("--track", type=int, default=None, help="override the config's tracker: 0 ground-truth poses, 1 extended ICP tracker, 2 icp")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
@@ -111,12 +124,20 @@ def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the newest committed
     `ncu --set full` capture (profiles/*_avg.json, written by tools/ncu_summary.py); {} when none is committed"""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_*_avg.json")))
+    import re
+
+    def key(path):   # (round, version) as numbers: "r01_ncu_full_v8" sorts before "r01_ncu_full_v26", and both before "r02_..."
+        m = re.search(r"r(\d+)_ncu_full_v(\d+)", os.path.basename(path))
+        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_*_avg.json")), key=key)
     if not files:
         return {}, None
     with open(files[-1]) as f:
         k = json.load(f)["kernels"]
-    return {name.split("::")[-1].split("<")[0]: v["dram_bytes_per_launch"] for name, v in k.items()}, os.path.basename(files[-1])
+    out = {}
+    for name, v in k.items():
+        out.setdefault(name.split("::")[-1].split("<")[0], v["dram_bytes_per_launch"])
+    return out, os.path.basename(files[-1])
 
 
 def load_peaks():
@@ -128,26 +149,36 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def make_frames(n_frames, device):
-    """synthetic Replica-shaped sequence, generated on the GPU: poses [n,4,4], rgba u8 [n,H,W,4], depth i16 [n,H,W]"""
+def window_of(total_frames, steps, warmup):
+    """(first warm-up frame, first timed frame, end of the timed window) inside a sequence of total_frames: the timed window ends
+    TAIL_FRAMES before the end of the sequence when it fits (frames 1750-1950 of 2000 for --steps 20 --warmup 5)"""
+    need = (steps + warmup) * FRAMES_PER_STEP
+    end = max(need, total_frames - TAIL_FRAMES)
+    end -= end % FRAMES_PER_STEP
+    return end - need, end - steps * FRAMES_PER_STEP, end
+
+
+def make_frames(n_frames, device, camera="replica", first=0):
+    """synthetic sequence of the config's camera shape, frames [first, n_frames) generated on `device`:
+    poses [n,4,4] (all n), rgba u8 [n-first,H,W,4], depth i16 [n-first,H,W]"""
     import torch
     from gps_slam_b200 import synthetic as syn
-    intr = syn.intrinsics("replica")
+    intr = syn.intrinsics(camera)
     poses = syn.trajectory(n_frames)
-    rgba = torch.empty((n_frames, intr["height"], intr["width"], 4), dtype=torch.uint8, device=device)
-    depth = torch.empty((n_frames, intr["height"], intr["width"]), dtype=torch.int16, device=device)
-    for i in range(n_frames):
+    rgba = torch.empty((n_frames - first, intr["height"], intr["width"], 4), dtype=torch.uint8, device=device)
+    depth = torch.empty((n_frames - first, intr["height"], intr["width"]), dtype=torch.int16, device=device)
+    for i in range(first, n_frames):
         r, d = syn.render_frame(poses[i], intr, device=device)
-        rgba[i], depth[i] = r, d
+        rgba[i - first], depth[i - first] = r, d
     return intr, poses, rgba, depth
 
 
 def run_reference(args):
-    """reference arm: the reference's InfiniTAM CPU engine, work_mode=recon, all host threads (rank 0 only)"""
+    """reference arm: the reference's InfiniTAM CPU engine, work_mode=recon, all host threads (rank 0 only).  Everything on this
+    arm runs on the host: the frames are generated with torch CPU ops, no kernel of this repository is involved."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import numpy as np
-    import torch
     from gps_slam_b200 import synthetic as syn
     from oracle import itm_ref
     kind = "fast" if itm_ref.available("fast") else "exact"
@@ -155,37 +186,41 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libitm_ref_*.so not built (needs /root/reference at build time)"}))
         return
     cores = os.cpu_count() or 1
-    intr = syn.intrinsics("replica")
+    cfg = CONFIGS[args.config if args.config in (2, 3, 4) else 2]
+    intr = syn.intrinsics(cfg["camera"])
+    total = args.frames or cfg["frames"]
     fps_step = args.ref_frames or 2           # bounded sample: a CPU frame costs ~0.1-1 s
     n = (args.warmup + args.steps) * fps_step
-    poses = syn.trajectory(n)
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
-    frames = [tuple(t.cpu().numpy() for t in syn.render_frame(poses[i], intr, device=dev)) for i in range(n)]
+    # the sample is taken where the GPU arm's timed window starts (same views, same visible-block counts), on a fresh map
+    first = min(window_of(max(total, n), args.steps, args.warmup)[1], max(total, n) - n)
+    poses = syn.trajectory(first + n)
+    frames = [tuple(t.numpy() for t in syn.render_frame(poses[first + i], intr, device="cpu")) for i in range(n)]
     ref = itm_ref.ItmRef(intr, tracker=0, threads=cores, kind=kind)
     k = 0
     for _ in range(args.warmup * fps_step):
-        ref.process_frame(frames[k][0], frames[k][1], syn.c2w_to_colmajor(poses[k]))
+        ref.process_frame(frames[k][0], frames[k][1], syn.c2w_to_colmajor(poses[first + k]))
         k += 1
     t0 = time.perf_counter()
     for _ in range(args.steps * fps_step):
-        ref.process_frame(frames[k][0], frames[k][1], syn.c2w_to_colmajor(poses[k]))
+        ref.process_frame(frames[k][0], frames[k][1], syn.c2w_to_colmajor(poses[first + k]))
         k += 1
     dt = time.perf_counter() - t0
     ref.close()
     fps = args.steps * fps_step / dt
-    sample = "%d frames/step x %d steps of the same synthetic Replica-shaped sequence, ITMBasicEngine CPU (%s build), use_gt_pose" % (
-        fps_step, args.steps, kind)
+    sample = "%d frames/step x %d steps, frames %d-%d of the same synthetic %dx%d sequence (where the GPU arm's timed window starts) on a fresh map, ITMBasicEngine CPU (%s build), use_gt_pose" % (
+        fps_step, args.steps, first + args.warmup * fps_step, first + n, intr["width"], intr["height"], kind)
     print(json.dumps({
         "impl": "reference", "metric": "slam_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "InfiniTAM CPU engine work_mode=recon (TSDF only), Replica 1200x680 synthetic", "frames_per_step": fps_step},
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (frames generated on the host)",
+        "config": {"workload": "InfiniTAM CPU engine work_mode=recon (TSDF only), %dx%d synthetic, sample of: %s" % (intr["width"], intr["height"], cfg["name"]),
+                   "frames_per_step": fps_step},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def eval_psnr(pipe, intr, poses, rgba, n_frames, dev, every=10):
-    """renderEvalImgs on every `every`-th training camera: PSNR = 20 log10(1 / sqrt(mse)) of the composited render against the
+def eval_psnr(pipe, intr, poses, rgba, frame_ids, dev):
+    """renderEvalImgs on the given training cameras: PSNR = 20 log10(1 / sqrt(mse)) of the composited render against the
     frame (scripts/utils/image_utils.py psnr), and of the TSDF colour raycast alone for context.  Not timed."""
     import torch
     H, W = intr["height"], intr["width"]
@@ -194,17 +229,19 @@ def eval_psnr(pipe, intr, poses, rgba, n_frames, dev, every=10):
     alpha = torch.empty((H, W), device=dev)
     ps, ps_tsdf = [], []
     with torch.cuda.stream(pipe.stream):
-        for i in range(0, n_frames, every):
+        for i in frame_ids:
             base = pipe.render_eval(poses[i], rgb, depth, alpha)
             gt = rgba[i][..., :3].float() / 255.0
             mse = float(((rgb.clamp(0, 1) - gt) ** 2).mean())
             mse_t = float(((base - gt) ** 2).mean())
             ps.append(20.0 * math.log10(1.0 / math.sqrt(mse)))
             ps_tsdf.append(20.0 * math.log10(1.0 / math.sqrt(mse_t)))
-    return {"psnr_db": sum(ps) / len(ps), "psnr_tsdf_only_db": sum(ps_tsdf) / len(ps_tsdf), "cameras": len(ps)}
+    return {"psnr_db": sum(ps) / len(ps), "psnr_tsdf_only_db": sum(ps_tsdf) / len(ps_tsdf), "cameras": len(ps),
+            "against": "the input frames (training views, every %d-th frame of the sequence)" % (frame_ids[1] - frame_ids[0] if len(frame_ids) > 1 else 1)}
 
 
-def cpu_baseline(intr, poses, rgba, depth, n_frames=6):
+def cpu_baseline(intr, poses, rgba, depth, first, n_frames=6):
+    """the reference InfiniTAM CPU engine on frames [first, first + n_frames] of the bench sequence (fresh map, 1 warm-up frame)"""
     import numpy as np
     from gps_slam_b200 import synthetic as syn
     from oracle import itm_ref
@@ -213,16 +250,21 @@ def cpu_baseline(intr, poses, rgba, depth, n_frames=6):
         return None
     cores = os.cpu_count() or 1
     ref = itm_ref.ItmRef(intr, tracker=0, threads=cores, kind=kind)
-    fr = [(rgba[i].cpu().numpy(), depth[i].cpu().numpy()) for i in range(n_frames + 1)]
-    ref.process_frame(fr[0][0], fr[0][1], syn.c2w_to_colmajor(poses[0]))
+    fr = [(rgba[first + i].cpu().numpy(), depth[first + i].cpu().numpy()) for i in range(n_frames + 1)]
+    ref.process_frame(fr[0][0], fr[0][1], syn.c2w_to_colmajor(poses[first]))
     t0 = time.perf_counter()
     for i in range(1, n_frames + 1):
-        ref.process_frame(fr[i][0], fr[i][1], syn.c2w_to_colmajor(poses[i]))
+        ref.process_frame(fr[i][0], fr[i][1], syn.c2w_to_colmajor(poses[first + i]))
     dt = time.perf_counter() - t0
     ref.close()
     return {"value": n_frames / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
-            "sample": "%d frames (after 1 warm-up) of the bench sequence through the reference InfiniTAM CPU engine "
-                      "(work_mode=recon: fusion + raycast per frame, use_gt_pose), %s build, OMP threads = cores" % (n_frames, kind)}
+            "sample": "%d frames (frames %d-%d of the bench sequence, after 1 warm-up, fresh map) through the reference InfiniTAM CPU engine "
+                      "(work_mode=recon: fusion + raycast per frame, use_gt_pose), %s build, OMP threads = cores" % (n_frames, first + 1, first + n_frames, kind)}
+
+
+def pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(q * len(xs)))] if xs else None
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -230,6 +272,11 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.config == 5:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import stress_sweep
+        stress_sweep.main(bench_line=True, args=args)
         return
     import numpy as np
     import torch
@@ -249,73 +296,111 @@ def main():
     E.load_library()
     from gps_slam_b200 import slam
     mode = args.mode or slam.DEFAULT_MODE
+    cfg = CONFIGS[args.config]
+    track = cfg["track"] if args.track is None else args.track
 
-    n_frames = (args.warmup + args.steps) * FRAMES_PER_STEP
-    intr, poses, rgba, depth = make_frames(n_frames, dev)
-    rgba_h = torch.empty(rgba.shape, dtype=rgba.dtype, pin_memory=True).copy_(rgba)
-    depth_h = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True).copy_(depth)
+    total = args.frames or cfg["frames"]
+    w0, t0f, t1f = window_of(total, args.steps, args.warmup)
+    total = max(total, t1f)
+    intr, poses, rgba, depth = make_frames(total, dev, cfg["camera"])
+    # host copies (pinned) of the frames the end-to-end leg uploads: its warm-up and timed window
+    rgba_h = torch.empty((t1f - w0,) + tuple(rgba.shape[1:]), dtype=rgba.dtype, pin_memory=True).copy_(rgba[w0:t1f])
+    depth_h = torch.empty((t1f - w0,) + tuple(depth.shape[1:]), dtype=depth.dtype, pin_memory=True).copy_(depth[w0:t1f])
     stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("GSB_MAIN_STREAM_PRIORITY", "-1")))
-    pipe = slam.SlamPipeline(intr, mode=mode, device=local, stream=stream, rank=rank, world=world, use_gt_pose=args.track == 0,
-                             tracker=args.track or 1)
+    pipe = slam.SlamPipeline(intr, mode=mode, device=local, stream=stream, rank=rank, world=world, use_gt_pose=track == 0,
+                             tracker=track or 1, gs_capacity=int(os.environ.get("GSB_GS_CAPACITY", str(1 << 22))))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_leg(resident):
-        """W warm-up + K timed steps from a fresh map; returns (ms, launches, stats)"""
+    def step(f, resident):
+        """one 10-frame local-optimisation cycle starting at frame f"""
+        for k in range(FRAMES_PER_STEP):
+            if resident:
+                pipe.process_frame(f + k, rgba, depth, poses, True)
+            else:
+                pipe.process_frame(f + k, rgba_h, depth_h, poses, False, frame_offset=w0)
+        pipe.end_of_step(resident)
+
+    def run_leg(resident, full):
+        """Pre-roll [0, w0) (always from resident frames, untimed for `value`), W warm-up steps, barrier + synchronize, K timed
+        steps, barrier + synchronize; with full=True the rest of the sequence follows and every step of the whole sequence is
+        bracketed by its own pair of events (the reference's FPS definition: all frames / time of the SLAMTrainCams loop)."""
         pipe.reset()
-        f = 0
         sampler = ClockSampler(local)
-        sampler.start()
+        begins, ends = [], []
+
+        def timed_step(f, res):
+            b = torch.cuda.Event(enable_timing=True)
+            b.record(stream)
+            step(f, res)
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            begins.append(b)
+            ends.append(e)
         with torch.cuda.stream(stream):
-            for _ in range(args.warmup):
-                for _ in range(FRAMES_PER_STEP):
-                    pipe.process_frame(f, rgba if resident else rgba_h, depth if resident else depth_h, poses, resident)
-                    f += 1
-                pipe.end_of_step(resident)
+            for f in range(0, w0, FRAMES_PER_STEP):
+                timed_step(f, True)
+            sampler.start()
+            for f in range(w0, t0f, FRAMES_PER_STEP):
+                timed_step(f, resident)
             barrier()
+            prof = full and os.environ.get("GSB_PROFILE_WINDOW") == "1"   # ncu --profile-from-start off: capture the timed window only
+            if prof:
+                torch.cuda.profiler.start()
             t_begin = time.time()
             l0 = E.launch_count()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            marks = [e0]
-            for _ in range(args.steps):
-                for _ in range(FRAMES_PER_STEP):
-                    pipe.process_frame(f, rgba if resident else rgba_h, depth if resident else depth_h, poses, resident)
-                    f += 1
-                pipe.end_of_step(resident)
-                marks.append(torch.cuda.Event(enable_timing=True))
-                marks[-1].record(stream)
-            e1 = marks[-1]
+            k0 = len(begins)
+            for f in range(t0f, t1f, FRAMES_PER_STEP):
+                timed_step(f, resident)
+            k1 = len(begins)
             barrier()
             t_end = time.time()
-            ms = e0.elapsed_time(e1)
-            run_leg.per_step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(len(marks) - 1)]
+            if prof:
+                torch.cuda.profiler.stop()
+            ms = begins[k0].elapsed_time(ends[k1 - 1])
             launches = E.launch_count() - l0
             clocks = sampler.stop(t_begin, t_end)
+            timed_each = [round(begins[i].elapsed_time(ends[i]), 3) for i in range(k0, k1)]
+            full_run = None
+            if full:
+                for f in range(t1f, total - total % FRAMES_PER_STEP, FRAMES_PER_STEP):
+                    timed_step(f, True)
+                torch.cuda.synchronize()
+                each = [begins[i].elapsed_time(ends[i]) for i in range(len(begins))]
+                n_fr = len(each) * FRAMES_PER_STEP
+                full_run = {"frames": n_fr, "fps": n_fr / (sum(each) * 1e-3), "ms_per_step_p50": round(pct(each, 0.5), 3), "ms_per_step_p95": round(pct(each, 0.95), 3),
+                            "ms_per_step_first": round(each[0], 3), "ms_per_step_last": round(each[-1], 3),
+                            "ms_per_step_every_20th": [round(x, 2) for x in each[::20]]}
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, launches, clocks
+        return ms, launches, clocks, timed_each, full_run
 
-    ms, launches, clocks = run_leg(True)
-    per_step_ms = list(run_leg.per_step_ms)
+    ms, launches, clocks, per_step_ms, full_run = run_leg(True, True)
     stats = pipe.stats()
-    psnr = eval_psnr(pipe, intr, poses, rgba, n_frames, dev) if mode == "train" else None
-    ms_e2e = run_leg(False)[0] if not args.no_e2e else float("nan")
+    if stats.get("overflow_flags"):
+        raise SystemExit("bench.py: capacity overflow (flags %d: 1 isects, 2 bwd items, 4 Gaussians) -- work was dropped, the run is invalid; "
+                         "raise gs_capacity / isect_capacity / item_capacity" % stats["overflow_flags"])
+    full_run.update(gaussians_final=stats.get("gaussians"), allocated_blocks_final=stats.get("allocated_blocks"), overflow_flags=stats.get("overflow_flags", 0))
+    psnr = eval_psnr(pipe, intr, poses, rgba, list(range(0, total, 40)), dev) if mode == "train" else None
+    tracking = pipe.tracking_stats(poses, total) if track else None
+    ms_e2e = run_leg(False, False)[0] if not args.no_e2e else float("nan")
+    stats_window = pipe.stats()
     frames = args.steps * FRAMES_PER_STEP
     fps = frames / (ms * 1e-3)
     fps_e2e = frames / (ms_e2e * 1e-3)
+    full_run["fps_e2e_window"] = fps_e2e
     h2d, d2h = pipe.io_bytes_per_step(FRAMES_PER_STEP)
 
     roofline = None
     if not args.no_kernel_timing and rank == 0:
         peak, peak_src = load_peaks()
         torch.cuda.nvtx.range_push("kernel_timing")   # ncu --nvtx --nvtx-include "kernel_timing/" captures steady-state launches
-        roofline = pipe.time_dominant_kernel(stream, peak, reps=args.timing_reps)
+        roofline = pipe.time_dominant_kernel(stream, peak, reps=args.timing_reps, fresh_frames=(rgba, depth, poses, t1f, min(total, t1f + 10)))
         torch.cuda.nvtx.range_pop()
         roofline["peak_source"] = peak_src
         traffic, src = ncu_traffic()
@@ -325,21 +410,26 @@ def main():
                 r["traffic_source"] = "profiles/" + src
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(intr, poses, rgba, depth)
+        cpu = cpu_baseline(intr, poses, rgba, depth, t0f)
 
     if rank == 0:
+        workload = "%s: %dx%d synthetic RGB-D, %d-frame sequence, office0.yaml hyper-parameters; work_mode=%s; timed window = frames %d-%d " \
+                   "after an untimed pre-roll of the map from frame 0 (%d warm-up steps included)" % (
+                       cfg["name"], intr["width"], intr["height"], total, mode, t0f, t1f, args.warmup)
         out = {
             "metric": "slam_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": pipe.scaling(), "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict({"workload": slam.workload_name(mode) if args.track == 0 else slam.workload_name(mode).replace(
-                                "use_gt_pose=true", "use_gt_pose=false: online ICP tracking, %s tracker" % ("extended" if args.track == 1 else "icp")),
-                            "parallelism": "single GPU" if world == 1 else "Gaussians sharded by spatial block over %d GPUs, one [H,W,5] "
-                                           "all-reduce per optimiser iteration; TSDF replicated" % world, "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
+            "config": dict({"workload": workload, "baseline_config": args.config,
+                            "parallelism": pipe.parallelism(), "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
                             "l2": "no explicit flush: every frame is new input (4.9 MB) and each step streams the visible voxel "
-                                  "blocks 10x (V x 8 KB per frame), working set > 126 MB L2", "quality": psnr, "ms_per_step_each": per_step_ms}, **stats),
+                                  "blocks 10x (V x 8 KB per frame), working set > 126 MB L2", "quality": psnr, "ms_per_step_each": per_step_ms,
+                            "full_run": full_run, "tracking": tracking}, **stats_window),
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "pinned host frames through gsb_tsdf_process_frame (H2D per frame); D2H once per 10-frame step: the pose estimate "
+                            "(64 B) and the last loss (8 B) -- the reference reads pose_d->GetInvM() on the host every frame, here the pose "
+                            "stays on the device between steps"},
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(out))

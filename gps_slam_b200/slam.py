@@ -139,6 +139,7 @@ class SlamPipeline:
         self.last_loss = None
         self.spawned_last = 0
         self._pose_host = np.zeros(16, np.float32)
+        self.track_err, self.track_iters = [], []
 
     def close(self):
         self.tsdf.close()
@@ -186,19 +187,22 @@ class SlamPipeline:
             self.tsdf.set_stream(self.sT.cuda_stream or 1)
 
     # ------------------------------------------------------------------------------------------------------------
-    def process_frame(self, idx, rgba_all, depth_all, poses, resident):
-        """one iteration of the SLAMTrainCams loop body (slam_pipeline.cpp:69-143)"""
+    def process_frame(self, idx, rgba_all, depth_all, poses, resident, frame_offset=0):
+        """one iteration of the SLAMTrainCams loop body (slam_pipeline.cpp:69-143); frame idx is rgba_all[idx - frame_offset]"""
         c2w = np.asarray(poses[idx], np.float32)
         if not self.use_gt_pose and self.tsdf.frames_processed() == 0:
             self.tsdf.set_pose(syn.c2w_to_colmajor(c2w))   # the reference re-bases the trajectory on frame 0; here frame 0 is given
         gt = syn.c2w_to_colmajor(c2w) if self.use_gt_pose else None
         if resident:
-            self.tsdf.ProcessFrameDevice(rgba_all[idx], depth_all[idx], gt)
+            self.tsdf.ProcessFrameDevice(rgba_all[idx - frame_offset], depth_all[idx - frame_offset], gt)
         else:
-            self.tsdf.ProcessFrame(rgba_all[idx], depth_all[idx], gt)
+            self.tsdf.ProcessFrame(rgba_all[idx - frame_offset], depth_all[idx - frame_offset], gt)
         if self.mode == "recon":
             return
         est = self.tsdf.pose()[1].reshape(4, 4).T.copy()      # est_pose = pose_d->GetInvM() as a row-major tensor (:81-82)
+        if not self.use_gt_pose:
+            self.track_err.append(float(np.linalg.norm(est[:3, 3] - c2w[:3, 3])))
+            self.track_iters.append(self.tsdf.tracker_result()[2])
         self.curr = (idx, c2w, est)
         self._update_frame_list(idx, c2w, est)
         c = self.cfg
@@ -383,6 +387,21 @@ class SlamPipeline:
                      last_isects=int(cnt[0]), last_visible=int(cnt[4]), overflow_flags=int(cnt[2]), cycles=self.cycles)
         return s
 
+    def parallelism(self):
+        if self.world == 1:
+            return "single GPU"
+        return ("Gaussians sharded by spatial block over %d GPUs, one [H,W,5] all-reduce per optimiser iteration; TSDF replicated" % self.world)
+
+    def tracking_stats(self, poses, total):
+        """online-tracking summary (BASELINE.json config 3): translation error of the tracked poses against the generator's, LM
+        iterations (= ICP evaluations: one 29-accumulator reduction each) per frame"""
+        if self.use_gt_pose or not self.track_err:
+            return None
+        e = np.asarray(self.track_err)
+        it = np.asarray(self.track_iters, np.float64)
+        return {"frames": int(len(e)), "ate_rmse_m": float(np.sqrt((e ** 2).mean())), "max_translation_error_m": float(e.max()),
+                "final_translation_error_m": float(e[-1]), "icp_evaluations_per_frame": float(it.mean())}
+
     def io_bytes_per_step(self, frames_per_step):
         return frames_per_step * self.W * self.H * 6, 64 + (8 if self.gs else 0)
 
@@ -405,11 +424,33 @@ class SlamPipeline:
                 ms.append(e0.elapsed_time(e1))
         return float(np.mean(ms)) * 1e-3
 
-    def time_dominant_kernel(self, stream, peak_gbs, reps=20):
+    def time_dominant_kernel(self, stream, peak_gbs, reps=20, fresh_frames=None):
         with self.single_stream():
-            return self._time_dominant_kernel(stream, peak_gbs, reps)
+            return self._time_dominant_kernel(stream, peak_gbs, reps, fresh_frames)
 
-    def _time_dominant_kernel(self, stream, peak_gbs, reps=20):
+    def _fresh_frame_stages(self, stream, fresh_frames):
+        """device time of every ProcessFrame stage on FRESH frames (the frames that follow the timed window), CUDA events between
+        the stages inside the engine: what the TSDF kernels cost inside the loop, where every frame changes every visible block"""
+        rgba, depth, poses, f0, f1 = fresh_frames
+        if f1 <= f0:
+            return None
+        self.tsdf.enable_stage_timing(True)
+        rows, vis = [], []
+        with torch.cuda.stream(stream):
+            for f in range(f0, f1):
+                c2w = np.asarray(poses[f], np.float32)
+                self.tsdf.ProcessFrameDevice(rgba[f], depth[f], syn.c2w_to_colmajor(c2w) if self.use_gt_pose else None)
+                rows.append(self.tsdf.stage_times())
+                vis.append(self.tsdf.counter(2))
+        self.tsdf.enable_stage_timing(False)
+        m = np.asarray(rows).mean(0) * 1e3
+        out = {k: float(v) for k, v in zip(("track", "allocate(6 kernels)", "integrate", "expected_depth(2)", "raycast", "icp_maps"), m)}
+        out.update(frames=len(rows), visible_blocks=float(np.mean(vis)))
+        if not self.use_gt_pose:
+            out["icp_evaluations_per_frame"] = float(np.mean(self.track_iters[-len(rows):])) if self.track_iters else None
+        return out
+
+    def _time_dominant_kernel(self, stream, peak_gbs, reps=20, fresh_frames=None):
         """Per-kernel device times (CUDA events on the launching stream, L2 flushed by a 256 MiB fill between launches) and the
         roofline entry of the kernel BASELINE.json names: the rasteriser backward in train mode (algorithmic bytes
         24*P + 48*I + 80*N_vis), the TSDF integrate kernel in recon mode (V*(4+16+2*4096) + 8*P)."""
@@ -420,15 +461,19 @@ class SlamPipeline:
         for name, st in (("tsdf_allocate(6 kernels)", 0), ("tsdf_integrate", 1), ("tsdf_expected_depth(2)", 2), ("tsdf_raycast", 3),
                          ("tsdf_icp_maps", 4)):
             table[name] = self._time(stream, lambda st=st: self.tsdf.run_stage(st), reps, flush) * 1e6
-        t_int = table["tsdf_integrate"] * 1e-6
-        alg_int = V * (4 + 16 + 2 * 4096) + 8 * P
+        fresh = self._fresh_frame_stages(stream, fresh_frames) if fresh_frames is not None else None
+        if fresh:
+            # the in-loop figure: fresh frames, events inside ProcessFrame (no L2 flush needed: every frame is new data and V x 8 KB
+            # of voxel blocks stream through)
+            t_int, Vf = fresh["integrate"] * 1e-6, fresh["visible_blocks"]
+            note = "mean over %d FRESH frames processed after the timed window (CUDA events between the stages inside gsb_tsdf_process_frame_device)" % fresh["frames"]
+        else:
+            t_int, Vf = table["tsdf_integrate"] * 1e-6, V
+            note = "timed by re-integrating the current frame (run_stage): a saturated map, few blocks change -- NOT the in-loop cost"
+        alg_int = Vf * (4 + 16 + 2 * 4096) + 8 * P
         integrate = {"kernel": "k_integrate_tma", "bound": "hbm", "achieved": alg_int / t_int / 1e9, "peak": peak_gbs, "unit": "GB/s",
                      "frac": alg_int / t_int / 1e9 / peak_gbs, "traffic": None, "algorithmic_bytes": alg_int, "avg_launch_us": t_int * 1e6,
-                     "units": {"visible_blocks": V, "pixels": P},
-                     "note": "timed by re-integrating the current frame (run_stage): the voxel weights of the steady-state map sit at maxW, so "
-                             "few blocks change and are written back; the same kernel on a fresh frame inside the loop takes 160-260 us "
-                             "(profiles/r01_ncu_launches_*.csv; ncu --set full of a loop launch: 107 M warp instructions, 64 % issue slots, "
-                             "112 MB read + 45 MB written, i.e. issue-bound, not HBM-bound)"}
+                     "units": {"visible_blocks": Vf, "pixels": P}, "note": note, "fresh_frame_stages_us": fresh}
         live = [c for c in self.opt_cams if c.depth_map is not None and c.image is not None]
         if self.mode != "train" or not live or self.n_gauss == 0:
             integrate["kernels_us"] = table
