@@ -463,6 +463,7 @@ extern "C" int gsb_gs_read(gsb_gs_t *e, int what, void *dst, size_t bytes)
     case GSB_GS_GRAD_DC: src = e->dbg.dc, avail = (size_t)e->cap * 12; break;
     case GSB_GS_GRAD_REST: src = e->dbg.rest, avail = (size_t)e->cap * 180; break;
     case GSB_GS_GRAD_OPAC: src = e->dbg.opac, avail = (size_t)e->cap * 4; break;
+    case GSB_GS_SPAWN_PIXELS: src = e->sb.pixOf, avail = P * 4; break;
     default: return gs_set_error(__FILE__, __LINE__, "bad read id");
     }
     if (!src)

@@ -46,7 +46,7 @@ class SpawnConfig(C.Structure):
 
 
 (GS_SPLAT_RECORDS, GS_SPLAT_GRADS, GS_TILE_OFFSETS, GS_FLATTEN_IDS, GS_V_OUT, GS_COUNTERS, GS_GRAD_MEANS, GS_GRAD_SCALES, GS_GRAD_QUATS,
- GS_GRAD_DC, GS_GRAD_REST, GS_GRAD_OPAC) = range(12)
+ GS_GRAD_DC, GS_GRAD_REST, GS_GRAD_OPAC, GS_SPAWN_PIXELS) = range(13)
 
 
 class EngineError(RuntimeError):
@@ -459,6 +459,10 @@ class GaussianEngine:
         c = self._cam(c2w)
         _check(self.L.gsb_gs_spawn(self.h_, C.byref(sc), _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(free_vertex_ptr),
                                    voxel_size, _ptr(depth_map), _ptr(color_map), _ptr(gt_rgb)))
+
+    def spawn_pixels(self, n):
+        """pixel index of each of the n Gaussians the last addGaussians appended (append order = raster order)"""
+        return self.read(GS_SPAWN_PIXELS, np.int32, (n,)) if n > 0 else np.zeros(0, np.int32)
 
     def run_stage(self, stage):
         _check(self.L.gsb_gs_run_stage(self.h_, stage))

@@ -75,9 +75,10 @@ def test_pyramid_and_single_evaluations(engine_lib, tracker):
         ref.close()
 
 
-@pytest.mark.parametrize("tracker,n_frames", [(1, 12), (2, 8)])
-def test_tracked_sequence(engine_lib, tracker, n_frames):
-    intr = syn.intrinsics("replica", 0.5)
+@pytest.mark.parametrize("tracker,n_frames,scale", [(1, 12, 0.5), (2, 8, 0.5), (1, 4, 1.0)])
+def test_tracked_sequence(engine_lib, tracker, n_frames, scale):
+    """scale 1.0: the full 1200x680 frames of BASELINE.json config 3 (4-level pyramid 1200x680 ... 150x85)"""
+    intr = syn.intrinsics("replica", scale)
     poses, frames = syn.sequence(n_frames, intr)
     eng, ref = make_pair(intr, tracker)
     try:
@@ -105,7 +106,8 @@ def test_tracked_sequence(engine_lib, tracker, n_frames):
             if i > 0:
                 res, score, iters = eng.tracker_result()
                 assert iters > 0 and np.isfinite(score)
-                assert res == ref.tracker_result() or tracker == 2, "tracking quality %d vs %d" % (res, ref.tracker_result())
+                # C5 UpdatePoseQuality: same verdict as the reference for both flavours
+                assert res == ref.tracker_result(), "tracking quality %d vs %d" % (res, ref.tracker_result())
     finally:
         eng.close()
         ref.close()
