@@ -71,8 +71,8 @@ def frame_to_float(rgba_u8, depth_mm_i16):
 
 def feature_gradient(img):
     H, W, Cc = img.shape
-    wx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]]).view(1, 1, 3, 3)
-    wy = torch.tensor([[-1., -2., -1.], [0., 0., 0.], [1., 2., 1.]]).view(1, 1, 3, 3)
+    wx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]]).view(1, 1, 3, 3).to(img)
+    wy = torch.tensor([[-1., -2., -1.], [0., 0., 0.], [1., 2., 1.]]).view(1, 1, 3, 3).to(img)
     p = img.permute(2, 0, 1).reshape(-1, 1, H, W)
     pad = torch.nn.functional.pad(p, (1, 1, 1, 1), mode="replicate")
     dx = torch.nn.functional.conv2d(pad, wx).squeeze(1).permute(1, 2, 0)
