@@ -397,7 +397,7 @@ def main():
     h2d, d2h = pipe.io_bytes_per_step(FRAMES_PER_STEP)
 
     roofline = None
-    if not args.no_kernel_timing and rank == 0:
+    if not args.no_kernel_timing:     # every rank takes part (with a communicator a training step is a collective); rank 0 reports
         peak, peak_src = load_peaks()
         torch.cuda.nvtx.range_push("kernel_timing")   # ncu --nvtx --nvtx-include "kernel_timing/" captures steady-state launches
         roofline = pipe.time_dominant_kernel(stream, peak, reps=args.timing_reps, fresh_frames=(rgba, depth, poses, t1f, min(total, t1f + 10)))

@@ -24,6 +24,7 @@ SOURCES = [
     ("gs_raw.cu", []),
     ("gs_ssim.cu", []),
     ("gs_knn.cu", []),
+    ("gs_comm.cu", []),
     ("gs_engine.cu", ["-fmad=false"]),
 ]
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gs_comm.h"
 #include "gs_math.cuh"
 
 namespace gs
@@ -74,7 +75,8 @@ enum RasterMode
 {
     RASTER_RAW = 0,    // render_colors [H,W,4] + alphas [H,W]                 (gsplat::rasterize_to_pixels_fwd_ges_tensor)
     RASTER_RENDER = 1, // composited rgb [H,W,3], depth [H,W], alpha [H,W]      (RawGaussianModel::gesForward outputs)
-    RASTER_TRAIN = 2   // composite + L1 loss + dL/d(render) packed as float4   (gesForward + computeLoss + backward head)
+    RASTER_TRAIN = 2,  // composite + L1 loss + dL/d(render) packed as float4   (gesForward + computeLoss + backward head)
+    RASTER_PUSH = 3    // multi-GPU: partial sums stored straight into the gather slots of peer ranks (gs_comm.h)
 };
 
 struct RasterIO
@@ -190,6 +192,9 @@ void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, 
 void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth /* nullable [H,W] */,
                 SplatGrad *grads, cudaStream_t st);
 void composite(int mode, const float *acc5 /* [P*4] render then [P] alphas */, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
+void raster_fwd_push(const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const RasterIO &io, const CommView *cvDev, bool pushAll,
+                     cudaStream_t st);
+void composite_exchange(int mode, const CommView &cv, const CommView *cvDev, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
 void pack_v_out(int P, const float *v_render4, const float *v_alphas, float4 *v_out, float *v_depth, cudaStream_t st);
 
 // ---- gs_raw.cu: depth-sorted front-to-back compositing (render_method "raw")

@@ -13,6 +13,7 @@
 #include "../../include/gpsslam_b200.h"
 #include "common.cuh"
 #include "gs.h"
+#include "gs_comm.h"
 #include "gs_spawn.h"
 
 using namespace gs;
@@ -31,9 +32,9 @@ struct gsb_gs
     SplatGrad *grads;
     float4 *aux;     // [cap*5] per-Gaussian SH basis / colour gradient / state flag between the two backward kernels
     Bins bins;
-    float4 *v_out;
+    float4 *v_out, *vOutOwn;   // vOutOwn / lossTileOwn: the engine's own buffers (v_out / lossTile point into the exchange segment with a communicator)
     float *v_depth;
-    float *lossTile;
+    float *lossTile, *lossTileOwn;
     double *lossDev;
     int *scanTmp;
     SpawnBuffers sb;
@@ -45,6 +46,7 @@ struct gsb_gs
     CamParams lastCam; // camera / image set of the last train step or stage-0 call (gsb_gs_run_stage)
     RasterIO lastIo;
     bool haveLast;
+    gsb_comm *comm;  // multi-GPU exchange (gsb_gs_set_comm); nullptr on one GPU
     void *knnWs;     // gs_knn.cu workspace, allocated on the first gsb_gs_dist_cuda2 call
     int knnCap;
     std::vector<void *> allocs;
@@ -124,6 +126,7 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     e->adamStep = 0;
     e->haveDbg = false;
     e->haveLast = false;
+    e->comm = nullptr;
     e->hostInts = nullptr, e->hostLoss = nullptr;
     GS_CUDA_OK(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
     e->stream = e->ownStream;
@@ -153,8 +156,10 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     rc |= dev_alloc(e, &e->bins.items, (size_t)e->bins.itemCap);
     rc |= dev_alloc(e, &e->bins.counters, (size_t)CNT_TOTAL);
     rc |= dev_alloc(e, &e->v_out, 2 * P);
+    e->vOutOwn = e->v_out;
     rc |= dev_alloc(e, &e->v_depth, P);
     rc |= dev_alloc(e, &e->lossTile, (size_t)e->T);
+    e->lossTileOwn = e->lossTile;
     rc |= dev_alloc(e, &e->lossDev, 1);
     rc |= dev_alloc(e, &e->scanTmp, (size_t)e->cap / 1024 + 2);
     {
@@ -210,6 +215,8 @@ extern "C" int gsb_gs_count(gsb_gs_t *e, int *n)
 {
     GS_CUDA_OK(cudaMemcpyAsync(e->hostInts, e->nDev, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (e->comm && *e->comm->errHost)
+        return gs_set_error(__FILE__, __LINE__, "multi-GPU exchange: a peer rank never reached a barrier (timed out)");
     e->nUpper = e->hostInts[0];
     if (n)
         *n = e->hostInts[0];
@@ -377,7 +384,16 @@ extern "C" int gsb_gs_render(gsb_gs_t *e, const float *c2w, float fx, float fy, 
     bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
     RasterIO io = make_io(e, ref_depth_dev, base_color_dev, nullptr);
     io.rgb = rgb_dev, io.depth = depth_dev, io.alphas = alpha_dev;
-    raster_fwd(RASTER_RENDER, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    if (e->comm)
+    {
+        // every rank needs the whole render: every tile goes to every rank, each rank composites all of it
+        raster_fwd_push(e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->comm->viewDev, true, e->stream);
+        comm_barrier(e->comm, e->stream);
+        composite_exchange(RASTER_RENDER, e->comm->view, e->comm->viewDev, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+        comm_barrier(e->comm, e->stream); // the gather slots may be overwritten by the peers' next push only after this
+    }
+    else
+        raster_fwd(RASTER_RENDER, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
     GS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -395,7 +411,16 @@ extern "C" int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float 
     bin_tiles(e->recs, e->nDev, e->nUpper, e->bins, e->tileW, e->tileH, e->stream);
     RasterIO io = make_io(e, ref_depth_dev, base_color_dev, gt_rgb_dev);
     e->lastCam = cam, e->lastIo = io, e->haveLast = true;
-    raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+    if (e->comm)
+    {
+        // reduce-scatter by the rasteriser's own stores, owner-side composite + loss, all-gather of dL/d(render) by the composite's stores
+        raster_fwd_push(e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->comm->viewDev, false, e->stream);
+        comm_barrier(e->comm, e->stream);
+        composite_exchange(RASTER_TRAIN, e->comm->view, e->comm->viewDev, e->W, e->H, e->tileW, e->tileH, io, e->stream);
+        comm_barrier(e->comm, e->stream);
+    }
+    else
+        raster_fwd(RASTER_TRAIN, e->recs, e->bins, e->W, e->H, e->tileW, e->tileH, io, e->stream);
     if (e->nUpper > 0)
         raster_bwd(e->recs, e->bins, e->W, e->H, io, nullptr, e->grads, e->stream);
     e->adamStep++;
@@ -515,7 +540,7 @@ extern "C" int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const flo
     const float *rRgb = e->spRgb, *rAlpha = e->spAlpha;
     if (sc->render_rgb_dev && sc->render_alpha_dev)
         rRgb = (const float *)sc->render_rgb_dev, rAlpha = (const float *)sc->render_alpha_dev; // the caller rendered (multi-GPU)
-    else if (e->nUpper > 0)
+    else if (e->nUpper > 0 || e->comm)   // (with a communicator every rank takes part in the render, even one without Gaussians)
         if (gsb_gs_render(e, c2w, fx, fy, cx, cy, depth_map_dev, color_map_dev, e->spRgb, e->spDepth, e->spAlpha))
             return 1;
     SpawnParams sp;
@@ -530,12 +555,32 @@ extern "C" int gsb_gs_spawn(gsb_gs_t *e, const gsb_spawn_config_t *sc, const flo
     sp.defaultOpacity = sc->default_opacity;
     sp.rank = sc->rank, sp.world = sc->world;
     sp.forceRender = (sc->render_rgb_dev && sc->render_alpha_dev) ? 1 : 0;
+    if (e->comm)
+        sp.rank = e->comm->rank, sp.world = e->comm->world, sp.forceRender = 1;
     spawn(sp, e->sb, (const float4 *)free_vertex_dev, depth_map_dev, color_map_dev, gt_rgb_dev, rRgb, rAlpha, e->p, e->nDev, e->cap,
           e->touched, e->bins.counters, e->stream);
     // host-side bound until the next gsb_gs_count
     long long up = (long long)e->nUpper + sp.P;
     e->nUpper = (int)(up > e->cap ? e->cap : up);
     GS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Multi-GPU: from here on gsb_gs_render / gsb_gs_train_step / gsb_gs_spawn exchange the partial images through the communicator's
+// peer-mapped segment (gs_comm.h); every rank must issue the same sequence of these calls.  The engine's dL/d(render) image and tile
+// losses move into the segment, where the owner ranks' composite kernels store them.
+extern "C" int gsb_gs_set_comm(gsb_gs_t *e, gsb_comm_t *comm)
+{
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    if (comm && (comm->W != e->W || comm->H != e->H || !comm->attached))
+        return gs_set_error(__FILE__, __LINE__, "communicator not attached, or created for another image size");
+    if (comm && comm->world == 1)
+        comm = nullptr;
+    GS_CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->comm = comm;
+    e->v_out = comm ? comm->view.vout[comm->rank] : e->vOutOwn;
+    e->lossTile = comm ? comm->view.lossTile[comm->rank] : e->lossTileOwn;
     return 0;
 }
 

@@ -30,7 +30,8 @@ constexpr int RB = 256; // splats per staged batch = threads per tile CTA
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 6) k_raster_fwd(const SplatRec *__restrict__ recs, const int *__restrict__ tileOffsets,
-                                                     const int *__restrict__ flattenSorted, int W, int H, int tileW, RasterIO io, float invCount)
+                                                     const int *__restrict__ flattenSorted, int W, int H, int tileW, RasterIO io, float invCount,
+                                                     const CommView *__restrict__ cv, int pushAll)
 {
     // one array, four planes (mean/opacity | log2-conic/depth | colour | alpha-extent box): a single base register addresses all of them
     __shared__ float4 sAll[4 * RB];
@@ -126,6 +127,27 @@ __global__ void __launch_bounds__(256, 6) k_raster_fwd(const SplatRec *__restric
         {
             reinterpret_cast<float4 *>(io.render4)[pix] = make_float4(a0, a1, a2, a3);
             io.alphas[pix] = w;
+        }
+        return;
+    }
+    if (MODE == RASTER_PUSH)
+    {
+        // the reduce-scatter IS this store: the tile's partial sums go to slot `rank` of the gather region of the rank that owns the
+        // tile (or of every rank, for a render that every rank needs in full), in tile-major order; a warp's 8 x 4 rectangle is four
+        // 128-byte runs of float4
+        if (inside)
+        {
+            const size_t t256 = cv->slotFloats / 5;
+            const size_t off = (size_t)tile * 256 + (size_t)((i - tyi * TILE) * TILE + (j - txi * TILE));
+            const size_t slot = (size_t)cv->rank * cv->slotFloats;
+            const float4 acc = make_float4(a0, a1, a2, a3);
+            const int q0 = pushAll ? 0 : comm_owner(*cv, tile), q1 = pushAll ? cv->world : q0 + 1;
+            for (int q = q0; q < q1; q++)
+            {
+                float *base = cv->gather[q] + slot;
+                reinterpret_cast<float4 *>(base)[off] = acc;
+                base[4 * t256 + off] = w;
+            }
         }
         return;
     }
@@ -443,6 +465,85 @@ __global__ void __launch_bounds__(256) k_composite(const float *__restrict__ acc
     }
 }
 
+// Multi-GPU epilogue (gs_comm.h): sums the G gather slots of a tile in rank order and finishes like k_composite.  TRAIN: launched over
+// the tiles this rank owns; the gradient record and the tile loss are stored into EVERY rank's v_out / lossTile.  RENDER: launched over
+// all tiles (every rank received every tile), outputs are local.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_composite_x(const CommView *__restrict__ cv, int tile0, int W, int H, int tileW, RasterIO io, float invCount)
+{
+    __shared__ float warpLoss[8];
+    const int tile = tile0 + blockIdx.x;
+    const int tyi = tile / tileW, txi = tile - tyi * tileW;
+    const int tid = threadIdx.x;
+    const int i = tyi * TILE + (tid >> 4), j = txi * TILE + (tid & 15);
+    const bool inside = (i < H) && (j < W);
+    const int pix = i * W + j;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, w = 0.f, rdRaw = 0.f;
+    if (inside)
+    {
+        const size_t t256 = cv->slotFloats / 5;
+        const size_t off = (size_t)tile * 256 + tid;
+        const float *mine = cv->gather[cv->rank];
+        for (int r = 0; r < cv->world; r++)
+        {
+            const float *base = mine + (size_t)r * cv->slotFloats;
+            const float4 a = __ldcg(reinterpret_cast<const float4 *>(base) + off);
+            a0 += a.x, a1 += a.y, a2 += a.z, a3 += a.w;
+            w += __ldcg(base + 4 * t256 + off);
+        }
+        rdRaw = __ldg(&io.refDepth[pix]);
+    }
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    float w1 = w + 1.0f;
+    if (inside)
+    {
+        const float *bc = io.baseColor + (size_t)pix * 3;
+        r0 = (a0 + __ldg(bc + 0) * 1.0f) / w1;
+        r1 = (a1 + __ldg(bc + 1) * 1.0f) / w1;
+        r2 = (a2 + __ldg(bc + 2) * 1.0f) / w1;
+    }
+    if (MODE == RASTER_RENDER)
+    {
+        if (inside)
+        {
+            float bw = rdRaw > 0.f ? 1.0f : 0.0f;
+            float *o = io.rgb + (size_t)pix * 3;
+            o[0] = r0, o[1] = r1, o[2] = r2;
+            io.depth[pix] = (a3 + rdRaw * bw) / (w + bw);
+            io.alphas[pix] = w;
+        }
+        return;
+    }
+    float lsum = 0.f;
+    if (inside)
+    {
+        const float *gt = io.gt + (size_t)pix * 3;
+        float d0 = r0 - __ldg(gt + 0), d1 = r1 - __ldg(gt + 1), d2 = r2 - __ldg(gt + 2);
+        lsum = fabsf(d0) + fabsf(d1) + fabsf(d2);
+        float v0 = d0 > 0.f ? invCount : (d0 < 0.f ? -invCount : 0.f);
+        float v1 = d1 > 0.f ? invCount : (d1 < 0.f ? -invCount : 0.f);
+        float v2 = d2 > 0.f ? invCount : (d2 < 0.f ? -invCount : 0.f);
+        float va = -(v0 * r0 + v1 * r1 + v2 * r2) / w1;
+        const float4 rec = make_float4(v0 / w1, v1 / w1, v2 / w1, va);
+        for (int q = 0; q < cv->world; q++)
+            cv->vout[q][2 * (size_t)pix] = rec; // the all-gather: one 16-byte store per peer (the depth cut next to it is rank-local)
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
+    if ((tid & 31) == 0)
+        warpLoss[tid >> 5] = lsum;
+    __syncthreads();
+    if (tid < cv->world)
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            s += warpLoss[k];
+        cv->lossTile[tid][tile] = s;
+    }
+}
+
 __global__ void k_pack_v_out(int P, const float *__restrict__ v_render4, const float *__restrict__ v_alphas, float4 *v_out, float *v_depth)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -460,11 +561,35 @@ void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, 
     const float invCount = 1.0f / (float)((size_t)3 * W * H);
     GS_COUNT_LAUNCHES(1);
     if (mode == RASTER_RAW)
-        k_raster_fwd<RASTER_RAW><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount);
+        k_raster_fwd<RASTER_RAW><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount, nullptr, 0);
     else if (mode == RASTER_RENDER)
-        k_raster_fwd<RASTER_RENDER><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount);
+        k_raster_fwd<RASTER_RENDER><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount, nullptr, 0);
     else
-        k_raster_fwd<RASTER_TRAIN><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount);
+        k_raster_fwd<RASTER_TRAIN><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, invCount, nullptr, 0);
+}
+
+// multi-GPU forward: partial sums into peer gather slots (cvDev: the CommView in device memory)
+void raster_fwd_push(const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const RasterIO &io, const CommView *cvDev, bool pushAll,
+                     cudaStream_t st)
+{
+    const int T = tileW * tileH;
+    GS_COUNT_LAUNCHES(1);
+    k_raster_fwd<RASTER_PUSH><<<T, 256, 0, st>>>(recs, bins.tileOffsets, bins.flattenSorted, W, H, tileW, io, 0.f, cvDev, pushAll ? 1 : 0);
+}
+
+void composite_exchange(int mode, const CommView &cv, const CommView *cvDev, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st)
+{
+    const int T = tileW * tileH;
+    const float invCount = 1.0f / (float)((size_t)3 * W * H);
+    GS_COUNT_LAUNCHES(1);
+    if (mode == RASTER_RENDER)
+        k_composite_x<RASTER_RENDER><<<T, 256, 0, st>>>(cvDev, 0, W, H, tileW, io, invCount);
+    else
+    {
+        const int t0 = cv.rank * cv.tilesPerRank, t1 = min(T, cv.rank == cv.world - 1 ? T : t0 + cv.tilesPerRank);
+        if (t1 > t0)
+            k_composite_x<RASTER_TRAIN><<<t1 - t0, 256, 0, st>>>(cvDev, t0, W, H, tileW, io, invCount);
+    }
 }
 
 void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth, SplatGrad *grads, cudaStream_t st)

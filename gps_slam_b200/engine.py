@@ -125,6 +125,15 @@ def load_library():
     L.gsb_gs_forward_partial.argtypes = [vp, vp, fl, fl, fl, fl, vp, vp, C.c_int]
     L.gsb_gs_render_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gsb_gs_train_finish.argtypes = [vp, vp, vp, vp, vp]
+    L.gsb_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.gsb_comm_export.argtypes = [vp, vp]
+    L.gsb_comm_attach.argtypes = [vp, vp]
+    L.gsb_comm_attach_local.argtypes = [vp, C.POINTER(vp)]
+    L.gsb_comm_barrier.argtypes = [vp, vp]
+    L.gsb_comm_error.argtypes = [vp]
+    L.gsb_comm_destroy.argtypes = [vp]
+    L.gsb_comm_destroy.restype = None
+    L.gsb_gs_set_comm.argtypes = [vp, vp]
     L.gsb_gs_raycast_maps.argtypes = [vp, vp, vp, vp, fl, vp, vp, vp]
     L.gsb_gs_frame_to_float.argtypes = [vp, vp, vp, vp, vp]
     L.gsb_tsdf_current_rgba_dev.argtypes = [vp]
@@ -322,6 +331,44 @@ class TsdfEngine:
         return self.read(IMAGE_FREE, np.uint8, (self.h, self.w, 4))
 
 
+class PeerComm:
+    """gsb_comm_t: this rank's exchange segment of the multi-GPU Gaussian path and the mapping of every peer's (csrc/gs_comm.h).
+    Ranks in different processes exchange the 64-byte IPC handles with export_handle() / attach(handles); engines inside one process
+    (tests) use attach_local(list of PeerComm in rank order)."""
+
+    def __init__(self, device, rank, world, width, height):
+        self.L = load_library()
+        self.rank, self.world = rank, world
+        h = C.c_void_p()
+        _check(self.L.gsb_comm_create(device, rank, world, width, height, C.byref(h)))
+        self.h_ = h
+
+    def export_handle(self):
+        buf = C.create_string_buffer(64)
+        _check(self.L.gsb_comm_export(self.h_, buf))
+        return buf.raw
+
+    def attach(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        _check(self.L.gsb_comm_attach(self.h_, C.c_char_p(blob)))
+
+    def attach_local(self, comms):
+        arr = (C.c_void_p * self.world)(*[c.h_ for c in comms])
+        _check(self.L.gsb_comm_attach_local(self.h_, arr))
+
+    def barrier(self, cuda_stream_ptr):
+        _check(self.L.gsb_comm_barrier(self.h_, C.c_void_p(cuda_stream_ptr)))
+
+    def error(self):
+        return int(self.L.gsb_comm_error(self.h_))
+
+    def close(self):
+        if self.h_:
+            self.L.gsb_comm_destroy(self.h_)
+            self.h_ = None
+
+
 PARAM_NAMES = ("means", "scales", "quats", "featuresDc", "featuresRest", "opacities")
 PARAM_WIDTH = dict(means=3, scales=3, quats=4, featuresDc=3, featuresRest=45, opacities=1)
 
@@ -419,6 +466,11 @@ class GaussianEngine:
                                         _ptr(base_color_dev), _ptr(gt_rgb_dev)))
 
     # ---- multi-GPU (Gaussians sharded across ranks): partial forward -> all-reduce by the caller -> finish
+    def set_comm(self, comm):
+        """attach a PeerComm: forward / train_step / addGaussians then run the whole multi-GPU iteration (exchange below the C ABI)"""
+        _check(self.L.gsb_gs_set_comm(self.h_, comm.h_ if comm is not None else None))
+        self.comm = comm
+
     def forward_partial(self, c2w, intr, ref_depth_dev, acc5, for_backward):
         c = self._cam(c2w)
         _check(self.L.gsb_gs_forward_partial(self.h_, _ptr(c), intr["fx"], intr["fy"], intr["cx"], intr["cy"], _ptr(ref_depth_dev), _ptr(acc5),

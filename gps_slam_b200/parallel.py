@@ -7,7 +7,10 @@ The reference is single-GPU (no collective call site anywhe
     image; ONE all-reduce(sum) of the partial accumulation image [H, W, 5] fp32 per optimiser iteration (16.3 MB at 1200x680)
     gives every rank the exact full image; composite / loss / dL/d(render) are recomputed redundantly, backward and Adam are
     rank-local (parameters are sharded, never replicated, so there is no parameter-gradient all-reduce at all);
-  * the TSDF map is replicated in this round: every rank fuses every frame (deterministic kernels -> identical maps, no exchange).
+  * the TSDF map is replicated: every rank fuses every frame (deterministic kernels -> identical maps, no exchange).
+Two exchange paths exist: "peer" (default) -- csrc/gs_comm.h: the rasteriser's epilogue stores every tile's partial sums straight into
+the owner rank's memory over NVLink, the owner composites and stores dL/d(render) into every rank's memory, flag barriers through peer
+memory, all below the C ABI -- and "nccl", the plain all-reduce of the [H,W,5] image between two C-ABI calls (kept for A/B timing).
 """
 import numpy as np
 import torch
@@ -40,6 +43,19 @@ def shard_params(params, rank, world):
         return params
     keep = owner_of(params["means"], world) == rank
     return {k: np.asarray(v)[keep] for k, v in params.items()}
+
+
+def make_peer_comm(device, rank, world, width, height):
+    """PeerComm of this rank with every peer's exchange segment mapped: the 64-byte CUDA IPC handles travel once through
+    torch.distributed (all_gather_object); afterwards no collective library is involved in the Gaussian path."""
+    from . import engine as E
+    comm = E.PeerComm(device, rank, world, width, height)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, comm.export_handle())
+        comm.attach(handles)
+        dist.barrier()
+    return comm
 
 
 def allreduce_sum_(t):

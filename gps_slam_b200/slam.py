@@ -80,7 +80,7 @@ class BufferPool:
 
 class SlamPipeline:
     def __init__(self, intr, mode="train", device=0, stream=None, rank=0, world=1, cfg=None, seed=42, gs_capacity=1 << 21, use_gt_pose=True,
-                 tracker=1, overlap=True):
+                 tracker=1, overlap=True, exchange=None, comm=None):
         """use_gt_pose=False: online tracking (TSDF.use_gt_pose: false) with the extended (1) or icp (2) tracker.
         world > 1: Gaussians sharded across ranks (parallel.py); torch.distributed must be initialised by the caller."""
         self.intr, self.mode, self.rank, self.world = intr, mode, rank, world
@@ -91,9 +91,17 @@ class SlamPipeline:
         self.tsdf = E.TsdfEngine(intr, voxel_size=c["voxel_size"], mu=c["trunc_dist"], view_frustum_min=c["viewFrustum_min"],
                                  view_frustum_max=c["viewFrustum_max"], tracker=0 if use_gt_pose else tracker, device=device)
         self.W, self.H = intr["width"], intr["height"]
-        self.acc5 = torch.empty(self.W * self.H * 5, dtype=torch.float32, device=self.device) if (world > 1 and mode == "train") else None
+        # multi-GPU exchange of the partial images: "peer" (stores into peer memory below the C ABI, csrc/gs_comm.h) or "nccl" (all-reduce
+        # between two C-ABI calls).  comm: an already attached PeerComm (tests with several engines in one process)
+        self.exchange = (exchange or os.environ.get("GSB_EXCHANGE", "peer")) if world > 1 else None
+        self.comm, self.own_comm = comm, False
+        self.acc5 = torch.empty(self.W * self.H * 5, dtype=torch.float32, device=self.device) if (self.exchange == "nccl" and mode == "train") else None
         self.sp_rgb = self.sp_depth = self.sp_alpha = None
         self.gs = E.GaussianEngine(self.W, self.H, capacity=gs_capacity, device=device) if mode == "train" else None
+        if self.gs and self.exchange == "peer":
+            if self.comm is None:
+                self.comm, self.own_comm = parallel.make_peer_comm(device, rank, world, self.W, self.H), True
+            self.gs.set_comm(self.comm)
         # Two streams (train mode): the TSDF side of the loop (fusion, raycasts, raycast -> tensor glue) runs on sT, the Gaussian side
         # (spawn, optimiser iterations, prune) on sG.  Nothing on the TSDF side depends on the Gaussians, so the 20 optimiser
         # iterations of a cycle (issue-bound rasteriser kernels) overlap with the fusion + raycasts of the following frames
@@ -145,6 +153,9 @@ class SlamPipeline:
         self.tsdf.close()
         if self.gs:
             self.gs.close()
+        if self.own_comm and self.comm is not None:
+            self.comm.close()
+            self.comm = None
 
     def _release(self, cam):
         self.pool.put(cam.depth_map, self.ev_gs)
@@ -294,7 +305,9 @@ class SlamPipeline:
         c = self.cfg
         before = self.n_gauss
         extra = {}
-        if self.world > 1:
+        if self.exchange == "peer":
+            extra = dict(rank=self.rank, world=self.world)       # the engine renders through the communicator itself
+        elif self.world > 1:
             # the sample mask needs the render of ALL Gaussians: partial forward -> all-reduce -> composite
             if self.sp_rgb is None:
                 self.sp_rgb, self.sp_depth, self.sp_alpha = self.pool.get((self.H, self.W, 3)), self.pool.get((self.H, self.W)), self.pool.get((self.H, self.W))
@@ -321,7 +334,7 @@ class SlamPipeline:
             current[i] = current[-1]
             current.pop()
             cam = cams[ci]
-            if self.world > 1:
+            if self.exchange == "nccl":
                 self.gs.forward_partial(cam.c2w_slam, self.intr, cam.depth_map, self.acc5, True)
                 self._allreduce_acc5()                  # the one collective of an iteration: [H,W,5] fp32 partial image
                 self.gs.train_finish(cam.depth_map, cam.color_map, cam.image, self.acc5)
@@ -336,7 +349,7 @@ class SlamPipeline:
 
     def _forward_all(self, cam, rgb, depth, alpha):
         """gesForward over the Gaussians of every rank"""
-        if self.world > 1:
+        if self.exchange == "nccl":
             self.gs.forward_partial(cam.c2w_slam, self.intr, cam.depth_map, self.acc5, False)
             self._allreduce_acc5()
             self.gs.render_finish(cam.depth_map, cam.color_map, self.acc5, rgb, depth, alpha)
@@ -390,7 +403,12 @@ class SlamPipeline:
     def parallelism(self):
         if self.world == 1:
             return "single GPU"
-        return ("Gaussians sharded by spatial block over %d GPUs, one [H,W,5] all-reduce per optimiser iteration; TSDF replicated" % self.world)
+        if self.exchange == "peer":
+            return ("Gaussians sharded by spatial block over %d GPUs; per optimiser iteration the rasteriser stores tile partial sums into the owner "
+                    "rank's memory over NVLink (reduce-scatter), the owner composites and stores dL/d(render) into every rank (all-gather), 2 flag "
+                    "barriers through peer memory, no NCCL call; TSDF replicated" % self.world)
+        return ("Gaussians sharded by spatial block over %d GPUs, one NCCL all-reduce of the [H,W,5] partial image per optimiser iteration; "
+                "TSDF replicated" % self.world)
 
     def tracking_stats(self, poses, total):
         """online-tracking summary (BASELINE.json config 3): translation error of the tracked poses against the generator's, LM

@@ -233,6 +233,25 @@ int gsb_gs_render_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *b
 int gsb_gs_train_finish(gsb_gs_t *e, const float *ref_depth_dev, const float *base_color_dev, const float *gt_rgb_dev,
                         const float *acc5_dev);
 
+/* Multi-GPU, exchange below the C ABI (no NCCL call between two entry points): a communicator owns this rank's exchange segment in
+ * device memory and maps every peer's (CUDA IPC over NVLink / NVSwitch when the ranks are processes; plain pointers inside one process).
+ * With a communicator attached to an engine, gsb_gs_render / gsb_gs_train_step / gsb_gs_spawn do the whole multi-GPU iteration
+ * themselves: the rasteriser stores each tile's partial sums into the gather slot of the tile's owner rank, the owner composites and
+ * stores dL/d(render) into every rank's gradient image; two flag barriers through peer memory per exchange; backward and Adam local.
+ * Every rank must issue the same sequence of these calls.  Bring-up (what a host does once, e.g. over MPI / torch.distributed):
+ *     gsb_comm_create(device, rank, world, W, H, &c);  gsb_comm_export(c, handle64);   all-gather the 64-byte handles;
+ *     gsb_comm_attach(c, handles);   (handles: world x 64 bytes, rank order)  gsb_gs_set_comm(engine, c);
+ * gsb_comm_attach_local takes the peers' communicators directly (several engines in one process). */
+typedef struct gsb_comm gsb_comm_t;
+int gsb_comm_create(int device, int rank, int world, int width, int height, gsb_comm_t **out);
+int gsb_comm_export(gsb_comm_t *c, void *handle64);
+int gsb_comm_attach(gsb_comm_t *c, const void *handles);
+int gsb_comm_attach_local(gsb_comm_t *c, gsb_comm_t *const *peers);
+int gsb_comm_barrier(gsb_comm_t *c, void *cuda_stream);       /* one flag barrier on the given stream (tests, host-level fences) */
+int gsb_comm_error(gsb_comm_t *c);                             /* non-zero once a barrier gave up waiting for a peer (~20 s)      */
+void gsb_comm_destroy(gsb_comm_t *c);
+int gsb_gs_set_comm(gsb_gs_t *e, gsb_comm_t *comm);            /* NULL detaches                                                   */
+
 /* ---- Staged entry points: one per gsplat::*_tensor function that RawGaussianModel::gesForward reaches through the autograd
  * wrappers of gsplat/gsplat_wapper.hpp, so that each wrapper can be re-pointed at this library on its own.
  * One camera (C = 1: the reference unsqueezes a camera dimension of size 1 everywhere, src/raw_gs_model.cpp:187); every pointer

@@ -206,3 +206,68 @@ def test_prune_keeps_adam_state_of_survivors(engine_lib):
         assert moved > 0
     finally:
         eng.close()
+
+
+def test_peer_exchange_matches_single_engine(engine_lib):
+    """the exchange below the C ABI (csrc/gs_comm.h) with two ranks living on one device: each engine holds one spatial shard, a
+    communicator pair maps the two exchange segments onto each other, and forward / train_step run the push - barrier - composite -
+    barrier sequence themselves.  Render, loss and per-Gaussian updates must equal the single-engine ones (re-associated fp32 sums),
+    and both ranks must hold bit-identical gradient images (the owner computes, everybody receives)."""
+    from gps_slam_b200 import parallel
+    from gps_slam_b200.engine import GaussianEngine, PeerComm
+    W, H, N = 320, 192, 2500
+    p = random_splats(N, seed=31)
+    c2w, K = camera(W, H, 31)
+    intr = gc.intr_of(K, W, H)
+    ref_depth, base, gt = scene_images(W, H, 31)
+    dev = torch.device("cuda", 0)
+    rd, bs, g = [torch.from_numpy(a).to(dev) for a in (ref_depth, base, gt)]
+    single = GaussianEngine(W, H, capacity=N)
+    shards = [GaussianEngine(W, H, capacity=N) for _ in range(2)]
+    comms = [PeerComm(0, r, 2, W, H) for r in range(2)]
+    try:
+        for c in comms:
+            c.attach_local(comms)
+        single.set_params(p)
+        single.initOptimizers()
+        rgb1, d1, a1 = torch.empty((H, W, 3), device=dev), torch.empty((H, W), device=dev), torch.empty((H, W), device=dev)
+        single.forward(c2w, intr, rd, bs, rgb1, d1, a1)
+        single.train_step(c2w, intr, rd, bs, g)
+        single.train_step(c2w, intr, rd, bs, g)
+        loss1 = single.loss()
+        after1 = single.get_params()
+        own = parallel.owner_of(p["means"], 2)
+        outs = []
+        for r in range(2):
+            shards[r].set_params(parallel.shard_params(p, r, 2))
+            shards[r].set_comm(comms[r])
+            shards[r].initOptimizers()
+            outs.append((torch.empty_like(rgb1), torch.empty_like(d1), torch.empty_like(a1)))
+        # every rank issues the same call sequence; the calls only enqueue, so one host thread can drive both ranks
+        for r in range(2):
+            shards[r].forward(c2w, intr, rd, bs, *outs[r])
+        for _ in range(2):
+            for r in range(2):
+                shards[r].train_step(c2w, intr, rd, bs, g)
+        for e in shards:
+            e.sync()
+        assert comms[0].error() == 0 and comms[1].error() == 0
+        for r in range(2):
+            gc.close_frac("peer rgb", outs[r][0].cpu().numpy(), rgb1.cpu().numpy(), 2e-6, 2e-6)
+            gc.close_frac("peer alpha", outs[r][2].cpu().numpy(), a1.cpu().numpy(), 2e-6, 2e-6)
+            gc.close_frac("peer depth", outs[r][1].cpu().numpy(), d1.cpu().numpy(), 2e-6, 2e-6)
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])
+        assert np.array_equal(shards[0].v_out().view(np.uint32), shards[1].v_out().view(np.uint32)), "ranks disagree on dL/d(render)"
+        assert abs(shards[0].loss() - loss1) < 1e-7 and shards[0].loss() == shards[1].loss()
+        for r in range(2):
+            got = shards[r].get_params()
+            for k in got:
+                exp = after1[k][own == r]
+                d = np.abs(got[k].reshape(len(exp), -1) - exp.reshape(len(exp), -1))
+                assert (d > 1e-6).mean() < 1e-2, (k, (d > 1e-6).mean())
+    finally:
+        single.close()
+        for e in shards:
+            e.close()
+        for c in comms:
+            c.close()
