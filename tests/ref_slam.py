@@ -173,10 +173,12 @@ def run_both(n_frames, scale=1.0, eval_every=10, device=0, verbose=False):
     res = {}
     renders = {}
     for name, cls in (("engine", slam.SlamPipeline), ("reference_kernels", RefSlamPipeline)):
-        stream = torch.cuda.Stream(device=dev)
-        pipe = cls(intr, mode="train", device=device, stream=stream, overlap=False, gs_capacity=1 << 20)
+        # Everything on the DEFAULT stream, as in the reference's program: its backward kernel is launched on the legacy default stream
+        # (rasterize_to_pixels_bwd_ges_new_parallel.cu:264, no stream argument) while the zero-fill of its outputs goes to torch's
+        # current stream -- on a side stream the two race and the kernel's atomics are partly wiped (seen as lost opacity gradients).
+        pipe = cls(intr, mode="train", device=device, stream=None, overlap=False, gs_capacity=1 << 20)
         counts, spawned = [], []
-        with torch.cuda.stream(stream):
+        if True:
             for f in range(n_frames):
                 pipe.process_frame(f, rgba, depth, poses, True)
                 if f % 10 == 0 and f > 0:

@@ -7,7 +7,7 @@ initNewGaussians, computeNormalMap, addGaussians, RawGaussianParams::init).
     GEMM whose summation order is libtorch's; ours is a fixed left-to-right dot product);
   * gsb_gs_spawn: the selected pixels are a subset of the reference's mask of the right size (the reference draws a randperm prefix,
     we keep each masked pixel with probability ratio -- a documented deviation), and GIVEN the selected pixels every parameter of the
-    new Gaussians follows the reference's init: means exact, scales (3-NN, clamp, z x 0.1, log) / quats / DC / opacity to fp32 rounding;
+    new Gaussians follows the reference's init: means exact, scales (3-NN, clamp, z x 0.1, log) / DC / opacity to fp32 rounding, the rotation through the axis it gives the Gaussian;
   * world = 2: the two ranks' spawns partition the world = 1 spawn and carry the same parameters (KNN over every rank's points).
 """
 import numpy as np
@@ -96,9 +96,23 @@ def check_spawn_against_oracle(gs, n_before, n_new, pix, vertex_map, image, norm
     s0 = np.exp(o["scales"][:, 0])
     assert (s0 < CFG["max_init_scale"] * 0.999).any() and (s0 >= CFG["max_init_scale"] * 0.999).any()
     assert np.allclose(np.exp(new["scales"][:, 2]), 0.1 * np.exp(new["scales"][:, 0]), rtol=1e-5)
-    # q and -q are the same rotation; the reference's formula fixes the sign (w = cos(angle/2) >= 0), so compare directly
-    dq = np.abs(new["quats"] - o["quats"])
-    assert dq.max() < 5e-5, ("quats", dq.max())
+    # The quaternion turns the z axis onto the surface normal (computeQuat).  The normal comes from Sobel differences of millimetre-spaced
+    # vertices that are metres from the origin (relative rounding ~1e-4, summation order of conv2d unspecified), and acos / the axis
+    # normalisation amplify that without bound where the normal is (anti)parallel to z -- there even the reference's own result is
+    # decided by rounding.  What the new Gaussian depends on is its covariance R diag(s^2, s^2, (0.1 s)^2) R^T, i.e. only R z: compare that,
+    # and the quaternions themselves where the construction is well conditioned.
+    def rz(q):
+        q = q / np.linalg.norm(q, axis=1, keepdims=True)   # (gsplat normalises the quaternion inside the projection)
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        return np.stack([2 * (x * z + w * y), 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)], 1)
+    # (a zero normal -- the reference zeroes it where the WORLD z of the vertex is <= 0 -- gives the non-unit (cos 45deg, 0, 0, 0) in both)
+    assert np.abs(np.linalg.norm(new["quats"], axis=1) - np.linalg.norm(o["quats"], axis=1)).max() < 1e-5
+    cosang = np.clip((rz(new["quats"]) * rz(o["quats"])).sum(1), -1, 1)
+    assert np.degrees(np.arccos(cosang)).max() < 0.3, ("rotated z axis", np.degrees(np.arccos(cosang)).max())
+    well = np.abs(rz(o["quats"])[:, 2]) < 0.9
+    assert well.sum() > 0.2 * len(well)
+    dq = np.abs(new["quats"] - o["quats"])[well]
+    assert dq.max() < 5e-4, ("quats", dq.max())
     assert np.abs(new["featuresDc"] - o["featuresDc"]).max() < 1e-6, "featuresDc"
     assert not new["featuresRest"].any()
     assert np.abs(new["opacities"] - o["opacities"]).max() < 1e-6, "opacities"
