@@ -373,6 +373,7 @@ def main():
             for f in range(t0f, t1f, FRAMES_PER_STEP):
                 timed_step(f, resident)
             k1 = len(begins)
+            pipe.flush_readback()
             barrier()
             t_end = time.time()
             if prof:

@@ -41,7 +41,9 @@ struct gsb_gs
     float *spRgb, *spDepth, *spAlpha; // render of the spawn camera (initNewGaussians)
     int adamStep;
     int *hostInts;   // pinned [8]
-    double *hostLoss; // pinned
+    double *hostLoss; // pinned [2]: [0] gsb_gs_loss, [1] gsb_gs_loss_begin / gsb_gs_loss_end
+    cudaEvent_t lossEv; // completion of the copy started by gsb_gs_loss_begin
+    bool lossPending;
     bool haveDbg;
     CamParams lastCam; // camera / image set of the last train step or stage-0 call (gsb_gs_run_stage)
     RasterIO lastIo;
@@ -101,6 +103,8 @@ extern "C" void gsb_gs_destroy(gsb_gs_t *e)
         cudaFreeHost(e->hostInts);
     if (e->hostLoss)
         cudaFreeHost(e->hostLoss);
+    if (e->lossEv)
+        cudaEventDestroy(e->lossEv);
     cudaStreamDestroy(e->ownStream);
     delete e;
 }
@@ -180,8 +184,11 @@ extern "C" int gsb_gs_create(const gsb_gs_config_t *cfg, gsb_gs_t **out)
     }
     if (!rc && cudaMallocHost((void **)&e->hostInts, 8 * sizeof(int)) != cudaSuccess)
         rc = gs_set_error(__FILE__, __LINE__, "pinned allocation failed");
-    if (!rc && cudaMallocHost((void **)&e->hostLoss, sizeof(double)) != cudaSuccess)
+    if (!rc && cudaMallocHost((void **)&e->hostLoss, 2 * sizeof(double)) != cudaSuccess)
         rc = gs_set_error(__FILE__, __LINE__, "pinned allocation failed");
+    e->lossPending = false;
+    if (!rc && cudaEventCreateWithFlags(&e->lossEv, cudaEventDisableTiming) != cudaSuccess)
+        rc = gs_set_error(__FILE__, __LINE__, "event creation failed");
     if (rc)
     {
         gsb_gs_destroy(e);
@@ -438,6 +445,29 @@ extern "C" int gsb_gs_loss(gsb_gs_t *e, double *loss)
     GS_CUDA_OK(cudaMemcpyAsync(e->hostLoss, e->lossDev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     GS_CUDA_OK(cudaStreamSynchronize(e->stream));
     *loss = *e->hostLoss;
+    return 0;
+}
+
+// The same read-back without stalling the host: gsb_gs_loss_begin enqueues the reduction and the 8-byte copy into pinned memory and
+// returns; gsb_gs_loss_end waits for that copy only (not for whatever was enqueued since) and returns the value.  A loop that reads
+// the loss of cycle k while cycle k+1 is already queued keeps the GPU fed.
+extern "C" int gsb_gs_loss_begin(gsb_gs_t *e)
+{
+    reduce_loss(e->lossTile, e->T, 1.0 / (3.0 * e->W * e->H), e->lossDev, e->stream);
+    GS_CUDA_OK(cudaMemcpyAsync(e->hostLoss + 1, e->lossDev, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    GS_CUDA_OK(cudaEventRecord(e->lossEv, e->stream));
+    e->lossPending = true;
+    return 0;
+}
+extern "C" int gsb_gs_loss_end(gsb_gs_t *e, double *loss)
+{
+    if (!e->lossPending)
+        return gs_set_error(__FILE__, __LINE__, "gsb_gs_loss_end without gsb_gs_loss_begin");
+    GS_CUDA_OK(cudaEventSynchronize(e->lossEv));
+    e->lossPending = false;
+    if (e->comm && *e->comm->errHost)
+        return gs_set_error(__FILE__, __LINE__, "multi-GPU exchange: a peer rank never reached a barrier (timed out)");
+    *loss = e->hostLoss[1];
     return 0;
 }
 

@@ -326,8 +326,11 @@ __global__ void __launch_bounds__(256) k_scatter_tiles(const SplatRec *__restric
 }
 
 // per tile: order the ids of every (tile, chunk) segment ascending; consumes (zeroes) the segment cursors
-constexpr int SORT_SMEM = 4096;
-constexpr int SORT_SEG_MAX = 256; // longer segments: sort the whole tile list cooperatively instead
+constexpr int SORT_SMEM = 8192;
+// A segment longer than this is not rank-sorted by one warp (n^2 / 32 steps on a single warp while the other seven idle -- Gaussians are
+// appended in raster order, so the ids of one tile cluster in a few id-range chunks and segments of several hundred ids are common in a
+// grown map): the whole tile list is sorted cooperatively by a bitonic network instead (n log^2 n / 256 steps per thread).
+constexpr int SORT_SEG_MAX = 64;
 __global__ void __launch_bounds__(256) k_sort_tiles(const int *__restrict__ tileOffsets, const int *__restrict__ segOff, int *segLen,
                                                      const int *__restrict__ flatten, int *flattenSorted)
 {
@@ -401,16 +404,14 @@ __global__ void __launch_bounds__(256) k_sort_tiles(const int *__restrict__ tile
         for (int k = 2; k <= n; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1)
             {
-                for (int i = tid; i < n; i += 256)
+                // one compare-exchange per loop step: pair p -> (i, i | j) with bit j of i clear
+                for (int p = tid; p < (n >> 1); p += 256)
                 {
-                    int ixj = i ^ j;
-                    if (ixj > i)
-                    {
-                        int a = s[i], b = s[ixj];
-                        bool asc = (i & k) == 0;
-                        if ((a > b) == asc)
-                            s[i] = b, s[ixj] = a;
-                    }
+                    const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                    const int a = s[i], b = s[i | j];
+                    const bool asc = (i & k) == 0;
+                    if ((a > b) == asc)
+                        s[i] = b, s[i | j] = a;
                 }
                 __syncthreads();
             }

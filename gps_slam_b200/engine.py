@@ -117,6 +117,8 @@ def load_library():
     L.gsb_gs_render.argtypes = [vp, vp, fl, fl, fl, fl, vp, vp, vp, vp, vp]
     L.gsb_gs_train_step.argtypes = [vp, vp, fl, fl, fl, fl, vp, vp, vp]
     L.gsb_gs_loss.argtypes = [vp, C.POINTER(C.c_double)]
+    L.gsb_gs_loss_begin.argtypes = [vp]
+    L.gsb_gs_loss_end.argtypes = [vp, C.POINTER(C.c_double)]
     L.gsb_gs_prune.argtypes = [vp, fl, fl, fl]
     L.gsb_gs_read.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.gsb_gs_enable_grad_dump.argtypes = [vp, C.c_int]
@@ -486,6 +488,15 @@ class GaussianEngine:
     def loss(self):
         v = C.c_double(0)
         _check(self.L.gsb_gs_loss(self.h_, C.byref(v)))
+        return v.value
+
+    def loss_begin(self):
+        """enqueue the read-back of the last step's loss (no host stall); loss_end() returns it"""
+        _check(self.L.gsb_gs_loss_begin(self.h_))
+
+    def loss_end(self):
+        v = C.c_double(0)
+        _check(self.L.gsb_gs_loss_end(self.h_, C.byref(v)))
         return v.value
 
     def prunePoints(self, min_opac, min_scale, max_scale):

@@ -148,6 +148,9 @@ class SlamPipeline:
         self.spawned_last = 0
         self._pose_host = np.zeros(16, np.float32)
         self.track_err, self.track_iters = [], []
+        if self.gs and getattr(self, "_loss_pending", False):
+            self.gs.loss_end()
+        self._loss_pending = False
 
     def close(self):
         self.tsdf.close()
@@ -370,11 +373,21 @@ class SlamPipeline:
         self._handover(self.sT, self.sG)
         self._handover(self.sG, self.sT)
         if not resident:
-            # what a caller reads back after a cycle: the pose estimate and the last loss (slam_pipeline.cpp:81-82, progress bar :283)
-            self.tsdf.sync()
+            # what a caller reads back after a cycle: the pose estimate (host-side state of the engine: 64 B) and the last loss
+            # (slam_pipeline.cpp:81-82, progress bar :283).  The loss travels through pinned memory one cycle behind: the copy of cycle
+            # k is enqueued here, the value of cycle k-1 -- long finished -- is collected, so the host keeps enqueueing ahead of the GPU
+            # instead of draining it every cycle.  flush_readback() collects the last one.
             self._pose_host = self.tsdf.pose()[1]
             if self.gs and self.cycles:
-                self.last_loss = self.gs.loss()
+                if self._loss_pending:
+                    self.last_loss = self.gs.loss_end()
+                self.gs.loss_begin()
+                self._loss_pending = True
+
+    def flush_readback(self):
+        if self.gs and self._loss_pending:
+            self.last_loss = self.gs.loss_end()
+            self._loss_pending = False
 
     def render_eval(self, c2w, rgb, depth, alpha):
         """renderEvalImgs body for one camera (slam_pipeline.cpp:588-660): free-view raycast + gesForward"""

@@ -197,6 +197,9 @@ int gsb_gs_render(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, f
 int gsb_gs_train_step(gsb_gs_t *e, const float *c2w, float fx, float fy, float cx, float cy, const float *ref_depth_dev,
                       const float *base_color_dev, const float *gt_rgb_dev);
 int gsb_gs_loss(gsb_gs_t *e, double *loss);                               /* loss["total"] of the last step; synchronises */
+/* the same in two halves: _begin enqueues the reduction + the 8-byte copy to pinned memory, _end waits for that copy only */
+int gsb_gs_loss_begin(gsb_gs_t *e);
+int gsb_gs_loss_end(gsb_gs_t *e, double *loss);
 /* SLAMPipeline::removeRedundantGs + prunePoints (remove_configs.low_opac_thres, small_scale_thres, large_scale_thres).
  * Like the reference's removeFromOptimizer (src/raw_gs_model.cpp:744-765) the surviving Gaussians keep their Adam moments, so
  * gsb_gs_train_step may follow directly; gsb_gs_init_optimizers before the prune makes it cheaper (no state to move). */

@@ -27,6 +27,7 @@ def run(n_frames, scale, world, rank, local):
         for f in range(n_frames):
             pipe.process_frame(f, rgba, depth, poses, True)
         pipe.end_of_step(False)
+        pipe.flush_readback()
         rgb, dep, alpha = torch.empty((H, W, 3), device=dev), torch.empty((H, W), device=dev), torch.empty((H, W), device=dev)
         ps = []
         for i in range(0, n_frames, 10):
