@@ -476,14 +476,6 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     const int N = *nDev;
     if (g0 >= N)
         return;
-    // SH coefficient run of the warp's 32 Gaussians by one TMA bulk copy, overlapped with the record / gradient loads below
-    if (lane == 0)
-    {
-        tma::mbar_init(&sBar[wid], 1);
-        tma::mbar_expect_tx(&sBar[wid], 32 * 45 * 4);
-        tma::load_1d(sRest[wid], p.rest + (size_t)g0 * 45, 32 * 45 * 4, &sBar[wid]);
-    }
-    __syncwarp();
     const bool inRange = g < N;
     const float4 q0 = inRange ? q0r : make_float4(0.f, 0.f, 0.f, 0.f);
     const int radius = __float_as_int(q0.w);
@@ -491,9 +483,18 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     const bool had = inRange && tch != 0;
     const unsigned full = 0xffffffffu;
     const unsigned visMask = __ballot_sync(full, vis);
+    // SH coefficient run of the warp's 32 Gaussians by one TMA bulk copy, overlapped with the projection re-computation below -- only
+    // when one of them is visible: the SH VJP is all that reads it, and in a grown map most warps are culled as a whole (Gaussians are
+    // appended in raster order, neighbours in id are neighbours in space)
+    if (lane == 0 && visMask)
+    {
+        tma::mbar_init(&sBar[wid], 1);
+        tma::mbar_expect_tx(&sBar[wid], 32 * 45 * 4);
+        tma::load_1d(sRest[wid], p.rest + (size_t)g0 * 45, 32 * 45 * 4, &sBar[wid]);
+    }
+    __syncwarp();
     float *rest = sRest[wid];
-    (void)visMask;
-    if (!vis)
+    if (!vis && visMask)
         tma::mbar_wait(&sBar[wid], 0); // every lane waits (the CTA must not retire with the copy in flight); visible lanes wait below
     float gm[3] = {0.f, 0.f, 0.f}, gsc[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gdc[3] = {0.f, 0.f, 0.f}, gop = 0.f;
     float basis[16], vcol[3] = {0.f, 0.f, 0.f};

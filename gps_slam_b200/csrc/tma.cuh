@@ -28,4 +28,12 @@ __device__ __forceinline__ void load_1d(void *dstSmem, const void *srcGmem, unsi
                  "l"(srcGmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk copy (bytes: multiple of 16, 16-byte aligned); generic-proxy writes to the source need fence_proxy_async() first
+__device__ __forceinline__ void store_1d(void *dstGmem, const void *srcSmem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGmem), "r"(smem_u32(srcSmem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 } // namespace tma

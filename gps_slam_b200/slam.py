@@ -120,7 +120,9 @@ class SlamPipeline:
         if mode == "train":
             # image buffers are recycled; allocate the working set up front so that no cudaMalloc (a device-wide sync) lands inside
             # the frame loop: window + keyframes hold an image, a depth map and a colour map each
-            pre = [self.pool.get((self.H, self.W, 3)) for _ in range(40)] + [self.pool.get((self.H, self.W)) for _ in range(24)]
+            # (every keyframe keeps its image for good -- the reference's GPU memory grows the same way -- so size for the keyframes of a
+            # few-thousand-frame sequence: 160 x 9.8 MB at 1200x680)
+            pre = [self.pool.get((self.H, self.W, 3)) for _ in range(160)] + [self.pool.get((self.H, self.W)) for _ in range(32)]
             for t in pre:
                 self.pool.put(t)
         self.seed = seed
