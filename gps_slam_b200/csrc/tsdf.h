@@ -19,7 +19,42 @@ struct Scene
     int E, numBlocks;
     float voxelSize, mu, vfmin, vfmax;
     int maxW;
+    // voxel-hash sharding: hash table / visibility / allocation are replicated (deterministic, every rank computes
+    // the same), the voxel DATA of a block lives on one rank only: owner = hashIndex(blockPos) mod world.
+    int rank, world;
+    int *visIdsOwn;          // [numBlocks]  the visible entries this rank owns (ascending); == visIds for world == 1
 };
+
+constexpr int SHARD_MAX_WORLD = 16;
+
+// what the sharded kernels see of the other ranks (peer-mapped device pointers, index = rank; own entry = local buffer)
+struct ShardView
+{
+    int rank, world;
+    const Voxel *vba[SHARD_MAX_WORLD];
+    unsigned char *visType[SHARD_MAX_WORLD];
+    float4 *rayLive[SHARD_MAX_WORLD];
+    float4 *rayFree[SHARD_MAX_WORLD];
+    uchar4 *imageFree[SHARD_MAX_WORLD];
+    float4 *pointsMap[SHARD_MAX_WORLD];
+    float4 *normalsMap[SHARD_MAX_WORLD];
+    unsigned *flags[SHARD_MAX_WORLD];   // [SHARD_MAX_WORLD] barrier arrival epochs, one per peer
+    float *icpXchg[SHARD_MAX_WORLD];    // [2][SHARD_MAX_WORLD][32] ICP partial sums (e3), double-buffered by sequence parity
+};
+
+__host__ __device__ inline int block_owner(int bx, int by, int bz, int world)
+{
+    return (int)((((unsigned)bx * 73856093u) ^ ((unsigned)by * 19349669u) ^ ((unsigned)bz * 83492791u)) & (unsigned)SDF_HASH_MASK) % world;
+}
+// rows [y0, y1) of the image a rank raycasts: contiguous slabs of whole 8-row tiles
+__host__ __device__ inline void slab_rows(int H, int rank, int world, int &y0, int &y1)
+{
+    const int tiles = (H + 7) / 8;
+    y0 = (int)((long long)tiles * rank / world) * 8;
+    y1 = (int)((long long)tiles * (rank + 1) / world) * 8;
+    if (y1 > H)
+        y1 = H;
+}
 
 struct Frame
 {
@@ -44,5 +79,10 @@ void raycast_stats(const Scene &s, const Camera &cam, int W, int H, const float2
 void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minmax, float4 *pointsRay, uchar4 *colour, bool modifyVisible,
              cudaStream_t st);
 void icp_maps(const Scene &s, const Camera &cam, int W, int H, const float4 *pointsRay, float4 *pointsMap, float4 *normalsMap, cudaStream_t st);
+// sharded forms (world > 1): this rank's slab of rows, voxels read from their owner's memory over NVLink; results are stored into
+// every rank's images (free view), resp. the two border rows into the neighbour slabs (live); visibility marks go to every rank
+void raycast_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, const float2 *minmax, bool live, cudaStream_t st);
+void icp_maps_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, bool pushAll, cudaStream_t st);
+void shard_barrier(const ShardView &v, unsigned epoch, int *errFlag, cudaStream_t st);
 
 } // namespace tsdf

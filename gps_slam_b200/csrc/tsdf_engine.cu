@@ -54,6 +54,17 @@ struct gsb_tsdf
     bool stageTiming;          // gsb_tsdf_enable_stage_timing: CUDA events between the stages of ProcessFrame
     cudaEvent_t stageEv[7];
     std::vector<void *> allocs;
+    // ---- voxel-hash sharding (world > 1): everything another rank reads or writes lives in ONE cudaMalloc segment, so that one CUDA IPC
+    // handle per rank maps it all: [flags | ICP exchange | visType | rayLive | rayFree | imageFree | pointsMap | normalsMap | voxel blocks]
+    int rank, world;
+    char *seg;
+    size_t segBytes, offXchg, offVis, offRayLive, offRayFree, offImage, offPoints, offNormals, offVba;
+    char *peer[tsdf::SHARD_MAX_WORLD];
+    bool ipcOpened[tsdf::SHARD_MAX_WORLD];
+    bool attached;
+    unsigned epoch;      // barriers issued so far (identical on every rank: SPMD call sequence)
+    int *errHost;        // pinned, mapped: set by a barrier (or an in-kernel exchange) that timed out
+    tsdf::ShardView view;
 };
 
 #define E_CUDA(call) GS_CUDA_OK(call)
@@ -79,10 +90,41 @@ extern "C" void gsb_tsdf_default_config(gsb_tsdf_config_t *c)
     c->integrate_variant = 0;
 }
 
-extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
+static size_t seg_align(size_t x) { return (x + 4095) / 4096 * 4096; }
+
+static void fill_shard_view(gsb_tsdf *e)
+{
+    tsdf::ShardView &v = e->view;
+    v.rank = e->rank, v.world = e->world;
+    for (int q = 0; q < e->world; q++)
+    {
+        char *b = e->peer[q];
+        v.flags[q] = (unsigned *)b;
+        v.icpXchg[q] = (float *)(b + e->offXchg);
+        v.visType[q] = (unsigned char *)(b + e->offVis);
+        v.rayLive[q] = (float4 *)(b + e->offRayLive);
+        v.rayFree[q] = (float4 *)(b + e->offRayFree);
+        v.imageFree[q] = (uchar4 *)(b + e->offImage);
+        v.pointsMap[q] = (float4 *)(b + e->offPoints);
+        v.normalsMap[q] = (float4 *)(b + e->offNormals);
+        v.vba[q] = (const Voxel *)(b + e->offVba);
+    }
+}
+
+static void shard_barrier(gsb_tsdf *e)
+{
+    e->epoch++;
+    tsdf::shard_barrier(e->view, e->epoch, e->errHost, e->stream);
+}
+
+extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out) { return gsb_tsdf_create_sharded(cfg, 0, 1, out); }
+
+extern "C" int gsb_tsdf_create_sharded(const gsb_tsdf_config_t *cfg, int rank, int world, gsb_tsdf_t **out)
 {
     if (!cfg || !out)
         return gs_set_error(__FILE__, __LINE__, "null argument");
+    if (world < 1 || world > tsdf::SHARD_MAX_WORLD || rank < 0 || rank >= world)
+        return gs_set_error(__FILE__, __LINE__, "invalid rank / world (world <= 16)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return gs_set_error(__FILE__, __LINE__, "no CUDA device: gpsslam_b200 has no CPU fallback");
@@ -104,8 +146,18 @@ extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
         delete e;
         return gs_set_error(__FILE__, __LINE__, "max_w > 255: the voxel's depth weight is one byte (ITMVoxel_s_rgb::w_depth)");
     }
+    if (world > 1 && e->cfg.num_blocks > (1 << 19))
+    {
+        delete e;
+        return gs_set_error(__FILE__, __LINE__, "sharded scene: num_blocks <= 524288 (28-bit voxel handles)");
+    }
     const int W = cfg->width, H = cfg->height, P = W * H;
+    e->rank = rank, e->world = world;
+    e->seg = nullptr, e->errHost = nullptr, e->epoch = 0, e->attached = world == 1;
+    memset(e->peer, 0, sizeof e->peer);
+    memset(e->ipcOpened, 0, sizeof e->ipcOpened);
     tsdf::Scene &s = e->scene;
+    s.rank = rank, s.world = world;
     s.E = SDF_TOTAL_ENTRIES;
     s.numBlocks = e->cfg.num_blocks;
     s.voxelSize = cfg->voxel_size, s.mu = cfg->mu, s.vfmin = cfg->view_frustum_min, s.vfmax = cfg->view_frustum_max;
@@ -114,10 +166,42 @@ extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
     e->stream = e->ownStream;
     int rc = 0;
     rc |= dev_alloc(e, &s.table, (size_t)s.E);
-    rc |= dev_alloc(e, &s.vba, (size_t)s.numBlocks * SDF_BLOCK_SIZE3);
     rc |= dev_alloc(e, &s.allocKey, (size_t)s.E);
-    rc |= dev_alloc(e, &s.visType, (size_t)s.E);
     rc |= dev_alloc(e, &s.visIds, (size_t)s.numBlocks);
+    if (world > 1)
+    {
+        e->offXchg = 4096;
+        e->offVis = e->offXchg + seg_align(2 * tsdf::SHARD_MAX_WORLD * 32 * sizeof(float));
+        e->offRayLive = e->offVis + seg_align((size_t)s.E);
+        e->offRayFree = e->offRayLive + seg_align((size_t)P * sizeof(float4));
+        e->offImage = e->offRayFree + seg_align((size_t)P * sizeof(float4));
+        e->offPoints = e->offImage + seg_align((size_t)P * sizeof(uchar4));
+        e->offNormals = e->offPoints + seg_align((size_t)P * sizeof(float4));
+        e->offVba = e->offNormals + seg_align((size_t)P * sizeof(float4));
+        e->segBytes = e->offVba + seg_align((size_t)s.numBlocks * SDF_BLOCK_SIZE3 * sizeof(Voxel));
+        rc |= dev_alloc(e, &e->seg, e->segBytes);
+        rc |= dev_alloc(e, &s.visIdsOwn, (size_t)s.numBlocks);
+        if (!rc)
+        {
+            cudaMemset(e->seg, 0, e->offVis);
+            if (cudaHostAlloc((void **)&e->errHost, sizeof(int), cudaHostAllocMapped) != cudaSuccess)
+                rc = gs_set_error(__FILE__, __LINE__, "pinned allocation failed");
+            else
+                *e->errHost = 0;
+            e->peer[rank] = e->seg;
+            s.visType = (unsigned char *)(e->seg + e->offVis);
+            s.vba = (Voxel *)(e->seg + e->offVba);
+            e->rayLive = (float4 *)(e->seg + e->offRayLive), e->rayFree = (float4 *)(e->seg + e->offRayFree);
+            e->imageFree = (uchar4 *)(e->seg + e->offImage);
+            e->pointsMap = (float4 *)(e->seg + e->offPoints), e->normalsMap = (float4 *)(e->seg + e->offNormals);
+        }
+    }
+    else
+    {
+        rc |= dev_alloc(e, &s.vba, (size_t)s.numBlocks * SDF_BLOCK_SIZE3);
+        rc |= dev_alloc(e, &s.visType, (size_t)s.E);
+        s.visIdsOwn = s.visIds;
+    }
     rc |= dev_alloc(e, &s.chunkCounts, (size_t)(s.E + 1023) / 1024);
     rc |= dev_alloc(e, &s.state, 8);
     rc |= dev_alloc(e, &e->depth_mm, (size_t)P);
@@ -126,11 +210,14 @@ extern "C" int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out)
     const int mm = ((W + 7) / 8) * ((H + 7) / 8);
     rc |= dev_alloc(e, &e->minmaxLive, (size_t)mm);
     rc |= dev_alloc(e, &e->minmaxFree, (size_t)mm);
-    rc |= dev_alloc(e, &e->rayLive, (size_t)P);
-    rc |= dev_alloc(e, &e->rayFree, (size_t)P);
-    rc |= dev_alloc(e, &e->pointsMap, (size_t)P);
-    rc |= dev_alloc(e, &e->normalsMap, (size_t)P);
-    rc |= dev_alloc(e, &e->imageFree, (size_t)P);
+    if (world == 1)
+    {
+        rc |= dev_alloc(e, &e->rayLive, (size_t)P);
+        rc |= dev_alloc(e, &e->rayFree, (size_t)P);
+        rc |= dev_alloc(e, &e->pointsMap, (size_t)P);
+        rc |= dev_alloc(e, &e->normalsMap, (size_t)P);
+        rc |= dev_alloc(e, &e->imageFree, (size_t)P);
+    }
     if (rc)
     {
         gsb_tsdf_destroy(e);
@@ -164,10 +251,90 @@ extern "C" void gsb_tsdf_destroy(gsb_tsdf_t *e)
     if (e->stageTiming)
         for (cudaEvent_t ev : e->stageEv)
             cudaEventDestroy(ev);
+    for (int q = 0; q < e->world; q++)
+        if (e->ipcOpened[q])
+            cudaIpcCloseMemHandle(e->peer[q]);
+    if (e->errHost)
+        cudaFreeHost(e->errHost);
     for (void *p : e->allocs)
         cudaFree(p);
     cudaStreamDestroy(e->ownStream);
     delete e;
+}
+
+// ---- sharded scene: mapping the other ranks' segments (same pattern as gsb_comm_*: CUDA IPC between processes, plain pointers between
+// engines of one process)
+extern "C" int gsb_tsdf_shard_export(gsb_tsdf_t *e, void *handle64)
+{
+    if (!e || !handle64 || e->world < 2)
+        return gs_set_error(__FILE__, __LINE__, "not a sharded engine");
+    cudaIpcMemHandle_t h;
+    E_CUDA(cudaIpcGetMemHandle(&h, e->seg));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int gsb_tsdf_shard_attach(gsb_tsdf_t *e, const void *handles)
+{
+    if (!e || !handles || e->world < 2)
+        return gs_set_error(__FILE__, __LINE__, "not a sharded engine");
+    E_CUDA(cudaSetDevice(e->cfg.device));
+    for (int q = 0; q < e->world; q++)
+    {
+        if (q == e->rank || e->ipcOpened[q])
+            continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)q * 64, 64);
+        void *p = nullptr;
+        E_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->peer[q] = (char *)p;
+        e->ipcOpened[q] = true;
+    }
+    fill_shard_view(e);
+    e->attached = true;
+    return 0;
+}
+
+extern "C" int gsb_tsdf_shard_attach_local(gsb_tsdf_t *e, gsb_tsdf_t *const *peers)
+{
+    if (!e || !peers || e->world < 2)
+        return gs_set_error(__FILE__, __LINE__, "not a sharded engine");
+    for (int q = 0; q < e->world; q++)
+    {
+        if (!peers[q] || peers[q]->world != e->world || peers[q]->rank != q || peers[q]->segBytes != e->segBytes)
+            return gs_set_error(__FILE__, __LINE__, "peer list does not match this engine");
+        if (peers[q]->cfg.device != e->cfg.device)
+        {
+            int can = 0;
+            E_CUDA(cudaDeviceCanAccessPeer(&can, e->cfg.device, peers[q]->cfg.device));
+            if (!can)
+                return gs_set_error(__FILE__, __LINE__, "no peer access between the devices");
+            E_CUDA(cudaSetDevice(e->cfg.device));
+            cudaError_t err = cudaDeviceEnablePeerAccess(peers[q]->cfg.device, 0);
+            if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled)
+                return gs_set_error(__FILE__, __LINE__, cudaGetErrorString(err));
+            cudaGetLastError();
+        }
+        e->peer[q] = peers[q]->seg;
+    }
+    fill_shard_view(e);
+    e->attached = true;
+    return 0;
+}
+
+extern "C" int gsb_tsdf_shard_error(gsb_tsdf_t *e) { return (e && e->errHost) ? *e->errHost : 0; }
+
+extern "C" int gsb_tsdf_shard_info(gsb_tsdf_t *e, int *rank, int *world, int *row0, int *row1)
+{
+    if (!e)
+        return gs_set_error(__FILE__, __LINE__, "null argument");
+    int y0, y1;
+    tsdf::slab_rows(e->cfg.height, e->rank, e->world, y0, y1);
+    if (rank) *rank = e->rank;
+    if (world) *world = e->world;
+    if (row0) *row0 = y0;
+    if (row1) *row1 = y1;
+    return 0;
 }
 
 extern "C" int gsb_tsdf_reset(gsb_tsdf_t *e)
@@ -250,6 +417,8 @@ static void refresh_camera(gsb_tsdf *e)
 static int process_resident(gsb_tsdf *e, const float *gt_c2w)
 {
     cudaStream_t st = e->stream;
+    if (!e->attached)
+        return gs_set_error(__FILE__, __LINE__, "sharded engine: the peer segments are not attached (gsb_tsdf_shard_attach)");
     auto mark = [&](int i)
     {
         if (e->stageTiming)
@@ -287,18 +456,35 @@ static int process_resident(gsb_tsdf *e, const float *gt_c2w)
     refresh_camera(e);
     mark(1);
     // --- fusion (ITMDenseMapper::ProcessFrame)
-    tsdf::allocate(e->scene, e->frame, e->cam, st);
+    tsdf::allocate(e->scene, e->frame, e->cam, st);   // replicated on every rank of a sharded scene (deterministic)
     mark(2);
-    tsdf::integrate(e->scene, e->frame, e->cam, e->cfg.integrate_variant, st);
+    tsdf::integrate(e->scene, e->frame, e->cam, e->cfg.integrate_variant, st);   // sharded: the visible blocks this rank owns
     mark(3);
     e->framesProcessed++;
     // --- ITMTrackingController::Prepare (always: requiresPointCloudRendering() is constant true)
     const int W = e->cfg.width, H = e->cfg.height;
     tsdf::expected_depth_live(e->scene, e->cam, W, H, e->minmaxLive, st);
     mark(4);
-    tsdf::raycast(e->scene, e->cam, W, H, e->minmaxLive, e->rayLive, nullptr, true, st);
-    mark(5);
-    tsdf::icp_maps(e->scene, e->cam, W, H, e->rayLive, e->pointsMap, e->normalsMap, st);
+    if (e->world == 1)
+    {
+        tsdf::raycast(e->scene, e->cam, W, H, e->minmaxLive, e->rayLive, nullptr, true, st);
+        mark(5);
+        tsdf::icp_maps(e->scene, e->cam, W, H, e->rayLive, e->pointsMap, e->normalsMap, st);
+    }
+    else
+    {
+        // Sharded scene.  Barrier A: every rank has integrated its blocks of this frame (and has finished reading what the raycast is
+        // about to overwrite).  The raycast reads the other ranks' voxels, stores its visibility marks into every rank and its border
+        // rows into the neighbour slabs.  Barrier B: all of that has landed, nobody reads voxels any more -> the next frame may
+        // integrate; the ICP maps of the slab follow (every rank receives every row while tracking is on, then barrier C).
+        shard_barrier(e);
+        tsdf::raycast_sharded(e->scene, e->view, e->cam, W, H, e->minmaxLive, true, st);
+        shard_barrier(e);
+        mark(5);
+        tsdf::icp_maps_sharded(e->scene, e->view, e->cam, W, H, e->trackingActive, st);
+        if (e->trackingActive)
+            shard_barrier(e);
+    }
     mark(6);
     e->pose_pointCloud = e->pose_d;
     e->agePointCloud = (e->agePointCloud == -1) ? -2 : 0;
@@ -345,8 +531,23 @@ extern "C" int gsb_tsdf_run_raycast(gsb_tsdf_t *e, const float *c2w, float fx, f
     cam.invM = p.get_invM();
     cam.fx = fx, cam.fy = fy, cam.cx = cx, cam.cy = cy;
     const int W = e->cfg.width, H = e->cfg.height;
-    tsdf::expected_depth_free(e->scene, cam, W, H, e->minmaxFree, e->stream);
-    tsdf::raycast(e->scene, cam, W, H, e->minmaxFree, e->rayFree, e->imageFree, false, e->stream);
+    if (e->world == 1)
+    {
+        tsdf::expected_depth_free(e->scene, cam, W, H, e->minmaxFree, e->stream);
+        tsdf::raycast(e->scene, cam, W, H, e->minmaxFree, e->rayFree, e->imageFree, false, e->stream);
+    }
+    else
+    {
+        // sharded scene: every rank marches its slab of rows and stores the result into every rank's free-view images.  The barrier in
+        // front says "every rank is done with the previous free-view images and with integrating"; the one behind says "all rows have
+        // landed everywhere and nobody reads voxels any more".
+        if (!e->attached)
+            return gs_set_error(__FILE__, __LINE__, "sharded engine: the peer segments are not attached (gsb_tsdf_shard_attach)");
+        tsdf::expected_depth_free(e->scene, cam, W, H, e->minmaxFree, e->stream);
+        shard_barrier(e);
+        tsdf::raycast_sharded(e->scene, e->view, cam, W, H, e->minmaxFree, false, e->stream);
+        shard_barrier(e);
+    }
     E_CUDA(cudaGetLastError());
     return 0;
 }
@@ -399,7 +600,7 @@ extern "C" int gsb_tsdf_frames_processed(gsb_tsdf_t *e) { return e->framesProces
 
 extern "C" int gsb_tsdf_counter(gsb_tsdf_t *e, int which, int *value)
 {
-    if (which < 0 || which > 3)
+    if (which < 0 || which > 7)
         return gs_set_error(__FILE__, __LINE__, "bad counter id");
     E_CUDA(cudaMemcpyAsync(value, e->scene.state + which, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     E_CUDA(cudaStreamSynchronize(e->stream));
@@ -470,8 +671,18 @@ extern "C" int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage)
     case 0: tsdf::allocate(e->scene, e->frame, e->cam, e->stream); break;
     case 1: tsdf::integrate(e->scene, e->frame, e->cam, e->cfg.integrate_variant, e->stream); break;
     case 2: tsdf::expected_depth_live(e->scene, e->cam, W, H, e->minmaxLive, e->stream); break;
-    case 3: tsdf::raycast(e->scene, e->cam, W, H, e->minmaxLive, e->rayLive, nullptr, true, e->stream); break;
-    case 4: tsdf::icp_maps(e->scene, e->cam, W, H, e->rayLive, e->pointsMap, e->normalsMap, e->stream); break;
+    case 3:
+        if (e->world == 1)
+            tsdf::raycast(e->scene, e->cam, W, H, e->minmaxLive, e->rayLive, nullptr, true, e->stream);
+        else
+            tsdf::raycast_sharded(e->scene, e->view, e->cam, W, H, e->minmaxLive, true, e->stream);   // no barriers: timing aid only
+        break;
+    case 4:
+        if (e->world == 1)
+            tsdf::icp_maps(e->scene, e->cam, W, H, e->rayLive, e->pointsMap, e->normalsMap, e->stream);
+        else
+            tsdf::icp_maps_sharded(e->scene, e->view, e->cam, W, H, false, e->stream);
+        break;
     default: return gs_set_error(__FILE__, __LINE__, "bad stage id");
     }
     E_CUDA(cudaGetLastError());

@@ -327,11 +327,13 @@ __device__ __forceinline__ bool block_visible(short bx, short by, short bz, cons
     return point_visible(M, proj, W, H, x, y, z);             // 1 0 1
 }
 
+// world > 1: the second scanned stream counts / ranks the visible entries whose voxel block this rank owns (visIdsOwn, state[6])
 __global__ void __launch_bounds__(SCAN_CTA) k_visible_count(unsigned char *visType, const HashEntry *__restrict__ table, int E, Mat4 M,
-                                                             float4 proj, float voxelSize, int W, int H, int2 *chunkCounts, int *state)
+                                                             float4 proj, float voxelSize, int W, int H, int2 *chunkCounts, int *state,
+                                                             int rank, int world)
 {
     int slot = blockIdx.x * SCAN_CTA + threadIdx.x;
-    int vis = 0;
+    int vis = 0, own = 0;
     if (slot == 0)
     {
         state[0] = state[4];
@@ -350,27 +352,48 @@ __global__ void __launch_bounds__(SCAN_CTA) k_visible_count(unsigned char *visTy
             }
         }
         vis = t > 0;
+        if (vis && world > 1)
+        {
+            HashEntry e = load_entry_cg(table, slot);
+            own = block_owner(e.px, e.py, e.pz, world) == rank;
+        }
     }
     int a = __syncthreads_count(vis);
+    int b = world > 1 ? __syncthreads_count(own) : 0;
     if (threadIdx.x == 0)
-        chunkCounts[blockIdx.x] = make_int2(a, 0);
+        chunkCounts[blockIdx.x] = make_int2(a, b);
 }
 
 __global__ void __launch_bounds__(SCAN_CTA) k_visible_compact(const unsigned char *__restrict__ visType, int E, int nChunks,
-                                                               const int2 *__restrict__ chunkCounts, int *visIds, int cap, int *nVis)
+                                                               const int2 *__restrict__ chunkCounts, int *visIds, int cap, int *nVis,
+                                                               const HashEntry *__restrict__ table, int myRank, int world, int *visIdsOwn,
+                                                               int *nVisOwn)
 {
     int slot = blockIdx.x * SCAN_CTA + threadIdx.x;
     int vis = slot < E && visType[slot] > 0;
+    int own = 0;
+    if (vis && world > 1)
+    {
+        HashEntry e = load_entry(table, slot);
+        own = block_owner(e.px, e.py, e.pz, world) == myRank;
+    }
     int2 pre = chunk_prefix(chunkCounts, blockIdx.x);
     int2 tot;
-    int2 rank = block_excl_scan2(vis, 0, tot);
+    int2 rank = block_excl_scan2(vis, own, tot);
     int pos = pre.x + rank.x;
     if (vis && pos < cap)
         visIds[pos] = slot;
+    if (own && pre.y + rank.y < cap)
+        visIdsOwn[pre.y + rank.y] = slot;
     if (blockIdx.x == nChunks - 1 && threadIdx.x == 0)
     {
         int n = pre.x + tot.x;
         *nVis = n < cap ? n : cap;
+        if (world > 1)
+        {
+            int m = pre.y + tot.y;
+            *nVisOwn = m < cap ? m : cap;
+        }
     }
 }
 
@@ -881,14 +904,35 @@ __global__ void k_project_all(const HashEntry *__restrict__ table, int E, Mat4 M
 // ------------------------------------------------------------------------------------------------------------
 // B7: raycast.  reference: castRay (Visualisation_Shared.h:122-221), readVoxel / readFromSDF_*
 // (ITMRepresentationAccess.h:77-232)
-struct VoxelCache
+// Voxel addressing.  A voxel is named by a 32-bit handle = index into the voxel block array (28 bits: up to 2^19 blocks) | owner rank << 28;
+// NO_VOXEL = not allocated.  VbaLocal: one array (single GPU, owner bits always 0).  VbaSharded: one array per rank, mapped over NVLink
+// (the hash table is replicated, a block's voxels live on rank hashIndex(blockPos) mod world only).
+constexpr unsigned NO_VOXEL = 0xffffffffu;
+struct VbaLocal
 {
-    int bx, by, bz, blockPtr;
+    const Voxel *vba;
+    __device__ __forceinline__ unsigned block_handle(int, int, int, int ptr) const { return (unsigned)ptr * SDF_BLOCK_SIZE3; }
+    __device__ __forceinline__ const Voxel *at(unsigned h) const { return vba + h; }
+};
+struct VbaSharded
+{
+    const ShardView *v;
+    __device__ __forceinline__ unsigned block_handle(int bx, int by, int bz, int ptr) const
+    {
+        return (unsigned)ptr * SDF_BLOCK_SIZE3 | ((unsigned)block_owner(bx, by, bz, v->world) << 28);
+    }
+    __device__ __forceinline__ const Voxel *at(unsigned h) const { return v->vba[h >> 28] + (h & 0x0fffffffu); }
 };
 
-// returns first 4 bytes of the voxel (sdf | w_depth<<16 | r<<24); vm = 0 not found, 1 cache hit, slot+1 hash hit
-__device__ __forceinline__ const Voxel *find_voxel(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int px, int py, int pz,
-                                                   int &vm, VoxelCache &c)
+struct VoxelCache
+{
+    int bx, by, bz;
+    unsigned block; // handle of the cached block's first voxel
+};
+
+// returns the voxel's handle; vm = 0 not found, 1 cache hit, slot+1 hash hit
+template <class A>
+__device__ __forceinline__ unsigned find_voxel(const A &vba, const HashEntry *__restrict__ table, int px, int py, int pz, int &vm, VoxelCache &c)
 {
     int bx = ((px < 0) ? px - SDF_BLOCK_SIZE + 1 : px) / SDF_BLOCK_SIZE;
     int by = ((py < 0) ? py - SDF_BLOCK_SIZE + 1 : py) / SDF_BLOCK_SIZE;
@@ -897,7 +941,7 @@ __device__ __forceinline__ const Voxel *find_voxel(const Voxel *__restrict__ vba
     if (bx == c.bx && by == c.by && bz == c.bz)
     {
         vm = 1;
-        return vba + c.blockPtr + lin;
+        return c.block + (unsigned)lin;
     }
     int idx = hash_index(bx, by, bz);
     while (true)
@@ -906,73 +950,72 @@ __device__ __forceinline__ const Voxel *find_voxel(const Voxel *__restrict__ vba
         if (e.px == bx && e.py == by && e.pz == bz && e.ptr >= 0)
         {
             c.bx = bx, c.by = by, c.bz = bz;
-            c.blockPtr = e.ptr * SDF_BLOCK_SIZE3;
+            c.block = vba.block_handle(bx, by, bz, e.ptr);
             vm = idx + 1;
-            return vba + c.blockPtr + lin;
+            return c.block + (unsigned)lin;
         }
         if (e.offset < 1)
             break;
         idx = SDF_BUCKET_NUM + e.offset - 1;
     }
     vm = 0;
-    return nullptr;
+    return NO_VOXEL;
 }
 
-__device__ __forceinline__ unsigned read_voxel_lo(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int px, int py, int pz,
-                                                  int &vm, VoxelCache &c)
+template <class A>
+__device__ __forceinline__ unsigned read_voxel_lo(const A &vba, const HashEntry *__restrict__ table, int px, int py, int pz, int &vm,
+                                                  VoxelCache &c)
 {
-    const Voxel *v = find_voxel(vba, table, px, py, pz, vm, c);
-    if (!v)
+    const unsigned h = find_voxel(vba, table, px, py, pz, vm, c);
+    if (h == NO_VOXEL)
         return 0x00007fffu; // default voxel: sdf = 32767, w_depth = 0, clr = 0
-    return __ldg(reinterpret_cast<const unsigned *>(v));
+    return __ldg(reinterpret_cast<const unsigned *>(vba.at(h)));
 }
 __device__ __forceinline__ float lo_sdf(unsigned lo) { return (float)(short)(lo & 0xffffu); }
 __device__ __forceinline__ float lo_w(unsigned lo) { return (float)((lo >> 16) & 0xffu); }
 
-__device__ __forceinline__ float sdf_uninterp(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, float3 p, int &vm, VoxelCache &c)
+template <class A>
+__device__ __forceinline__ float sdf_uninterp(const A &vba, const HashEntry *__restrict__ table, float3 p, int &vm, VoxelCache &c)
 {
     int ix = (int)(p.x < 0 ? p.x - 0.5f : p.x + 0.5f), iy = (int)(p.y < 0 ? p.y - 0.5f : p.y + 0.5f), iz = (int)(p.z < 0 ? p.z - 0.5f : p.z + 0.5f);
     unsigned lo = read_voxel_lo(vba, table, ix, iy, iz, vm, c);
-    return lo_sdf(lo) / 32767.0f;
+    return div_32767(lo_sdf(lo)); // == lo_sdf / 32767.0f for every short (exhaustive proof: tools/div_proof)
 }
 
 // The 8 corners of a trilinear read are resolved first (same order and therefore same cache / hash-walk sequence as the reference's
 // eight readVoxel calls), then all 8 voxels are requested together, then combined with the reference's arithmetic: one memory round
-// trip per interpolated read instead of four (sdf) or eight (colour) chained ones.  -1 = corner not allocated.
-__device__ __forceinline__ void find_corners(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int x, int y, int z, int &vm,
-                                             VoxelCache &c, int (&off)[8])
+// trip per interpolated read instead of four (sdf) or eight (colour) chained ones.  NO_VOXEL = corner not allocated.
+template <class A>
+__device__ __forceinline__ void find_corners(const A &vba, const HashEntry *__restrict__ table, int x, int y, int z, int &vm, VoxelCache &c,
+                                             unsigned (&off)[8])
 {
-    const Voxel *v0 = find_voxel(vba, table, x, y, z, vm, c);
-    off[0] = v0 ? (int)(v0 - vba) : -1;
+    off[0] = find_voxel(vba, table, x, y, z, vm, c);
     if (((x & 7) != 7) && ((y & 7) != 7) && ((z & 7) != 7))
     {
         // all 8 corners lie in the block of corner 0 (2 reads out of 3): the seven remaining readVoxel calls would be cache hits on it
         // (or walk the same empty hash chain) without changing any state, so their addresses follow from the first
 #pragma unroll
         for (int k = 1; k < 8; k++)
-            off[k] = v0 ? off[0] + (k & 1) + ((k >> 1) & 1) * SDF_BLOCK_SIZE + (k >> 2) * SDF_BLOCK_SIZE * SDF_BLOCK_SIZE : -1;
+            off[k] = off[0] != NO_VOXEL ? off[0] + (unsigned)((k & 1) + ((k >> 1) & 1) * SDF_BLOCK_SIZE + (k >> 2) * SDF_BLOCK_SIZE * SDF_BLOCK_SIZE)
+                                        : NO_VOXEL;
         return;
     }
 #pragma unroll
     for (int k = 1; k < 8; k++)
-    {
-        const Voxel *v = find_voxel(vba, table, x + (k & 1), y + ((k >> 1) & 1), z + (k >> 2), vm, c);
-        off[k] = v ? (int)(v - vba) : -1;
-    }
+        off[k] = find_voxel(vba, table, x + (k & 1), y + ((k >> 1) & 1), z + (k >> 2), vm, c);
 }
 
-template <bool withConf>
-__device__ __forceinline__ float sdf_interp(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, float3 p, int &vm, VoxelCache &c,
-                                            float &conf)
+template <bool withConf, class A>
+__device__ __forceinline__ float sdf_interp(const A &vba, const HashEntry *__restrict__ table, float3 p, int &vm, VoxelCache &c, float &conf)
 {
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     float cx = p.x - fx, cy = p.y - fy, cz = p.z - fz;
-    int off[8];
+    unsigned off[8];
     find_corners(vba, table, (int)fx, (int)fy, (int)fz, vm, c, off);
     unsigned lo[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
-        lo[k] = off[k] >= 0 ? __ldg(reinterpret_cast<const unsigned *>(vba + off[k])) : 0x00007fffu; // default voxel: sdf = 32767, w_depth = 0
+        lo[k] = off[k] != NO_VOXEL ? __ldg(reinterpret_cast<const unsigned *>(vba.at(off[k]))) : 0x00007fffu; // default voxel: sdf = 32767, w_depth = 0
     float res1, res2, r1c = 0, r2c = 0;
     res1 = (1.0f - cx) * lo_sdf(lo[0]) + cx * lo_sdf(lo[1]);
     if (withConf) r1c = (1.0f - cx) * lo_w(lo[0]) + cx * lo_w(lo[1]);
@@ -984,28 +1027,30 @@ __device__ __forceinline__ float sdf_interp(const Voxel *__restrict__ vba, const
     if (withConf) r2c = (1.0f - cy) * r2c + cy * ((1.0f - cx) * lo_w(lo[6]) + cx * lo_w(lo[7]));
     vm = 1;
     if (withConf) conf = (1.0f - cz) * r1c + cz * r2c;
-    return ((1.0f - cz) * res1 + cz * res2) / 32767.0f;
+    return div_32767((1.0f - cz) * res1 + cz * res2); // |x| <= 32767: inside the proven range of the exact form
 }
 
 // readFromSDF_color4u_interpolated (ITMRepresentationAccess.h:344-424) + drawPixelColour (Visualisation_Shared.h:386-396)
-__device__ __forceinline__ uchar4 colour_interp(const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, float3 p)
+template <class A>
+__device__ __forceinline__ uchar4 colour_interp(const A &vba, const HashEntry *__restrict__ table, float3 p)
 {
-    VoxelCache c = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1};
+    VoxelCache c = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0u};
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     float cx = p.x - fx, cy = p.y - fy, cz = p.z - fz;
     float rx = 0, ry = 0, rz = 0, wsum = 0;
-    int vm, off[8];
+    int vm;
+    unsigned off[8];
     find_corners(vba, table, (int)fx, (int)fy, (int)fz, vm, c, off);
     uint2 raw[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
-        raw[k] = off[k] >= 0 ? __ldg(reinterpret_cast<const uint2 *>(vba + off[k])) : make_uint2(0u, 0u);
+        raw[k] = off[k] != NO_VOXEL ? __ldg(reinterpret_cast<const uint2 *>(vba.at(off[k]))) : make_uint2(0u, 0u);
 #pragma unroll
     for (int k = 0; k < 8; k++)
     {
         int ox = k & 1, oy = (k >> 1) & 1, oz = (k >> 2) & 1;
         unsigned wc = (raw[k].y >> 16) & 0xffu;   // 0 for a missing corner: skipped like the reference's `continue`
-        if (off[k] >= 0 && wc >= 1u)
+        if (off[k] != NO_VOXEL && wc >= 1u)
         {
             float w = (ox ? cx : (1.0f - cx)) * (oy ? cy : (1.0f - cy)) * (oz ? cz : (1.0f - cz));
             rx += w * (float)((raw[k].x >> 24) & 0xffu);
@@ -1015,7 +1060,7 @@ __device__ __forceinline__ uchar4 colour_interp(const Voxel *__restrict__ vba, c
         }
     }
     rx /= wsum, ry /= wsum, rz /= wsum;
-    rx /= 255.0f, ry /= 255.0f, rz /= 255.0f;
+    rx = div_255(rx), ry = div_255(ry), rz = div_255(rz); // == x / 255.0f (x >= +0 or NaN here; exhaustive proof: tools/div_proof)
     uchar4 o;
     // (uchar) of NaN is UB on the host; x86 cvttss2si and the GPU both give 0 after truncation to 8 bits
     o.x = (unsigned char)(int)(rx * 255.0f);
@@ -1025,23 +1070,43 @@ __device__ __forceinline__ uchar4 colour_interp(const Voxel *__restrict__ vba, c
     return o;
 }
 
-// STATS (diagnostic build of the same loop, gsb_tsdf_raycast_stats): visType is reinterpreted as unsigned long long[8] totals --
-// rays, march steps, steps in unallocated space, trilinear reads, steps that changed voxel block, warp-max steps summed over warps, warps
-template <bool modifyVisible, bool withColour, bool STATS = false>
-__global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay, uchar4 *__restrict__ colourOut, unsigned char *visType,
-                                                  const Voxel *__restrict__ vba, const HashEntry *__restrict__ table, int W, int H, Mat4 invM,
-                                                  float4 invProj /* 1/fx 1/fy -cx -cy */, float oneOverVoxelSize, float mu,
-                                                  const float2 *__restrict__ minmax, int mmW)
+// where the visibility marks of the live raycast go (modifyVisible): the local entriesVisibleType, or -- sharded -- every rank's copy.
+// The copies are identical when the raycast starts (the allocation pass is replicated), so a mark that does not change the local byte does
+// not change any other rank's either and is not sent; the rare ones that do (a block the ray touches that the depth image did not mark)
+// are stored into every rank's array (idempotent byte stores over NVLink, ordered by the barrier that follows the raycast).
+struct MarkLocal
 {
-    // 32x8 pixel tile per CTA, one 8x4 pixel patch per warp: the 32 rays of a warp share one cell of the 1/8-resolution range
-    // image and march through the same few voxel blocks, so they take nearly the same number of steps (a warp runs for as long
-    // as its slowest ray) and their hash / voxel reads hit the same lines; each patch row is still one 128-byte store.
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
-    int y = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
-    if (x >= W || y >= H)
-        return;
-    float2 mm = __ldg(&minmax[(x >> 3) + (y >> 3) * mmW]);
+    unsigned char *visType;
+    __device__ __forceinline__ void operator()(int slot) const { visType[slot] = 1; }
+};
+struct MarkAll
+{
+    const ShardView *v;
+    __device__ __forceinline__ void operator()(int slot) const
+    {
+        if (*(volatile unsigned char *)(v->visType[v->rank] + slot) == 1)
+            return;
+        for (int q = 0; q < v->world; q++)
+            v->visType[q][slot] = 1;
+    }
+};
+struct MarkNone
+{
+    __device__ __forceinline__ void operator()(int) const {}
+};
+
+struct RayCounters
+{
+    int nSteps, nMiss, nInterp, nBlock;
+};
+
+// castRay for pixel (x, y): pt = hit point in voxel units, conf; returns found
+template <bool modifyVisible, bool STATS, class A, class Mark>
+__device__ __forceinline__ bool cast_ray(const A &vba, const HashEntry *__restrict__ table, const Mark &mark, int x, int y, const Mat4 &invM,
+                                         float4 invProj /* 1/fx 1/fy -cx -cy */, float oneOverVoxelSize, float mu, float2 mm, float3 &pt,
+                                         float &conf, RayCounters &cnt)
+{
+    const int lane = threadIdx.x & 31;
     float stepScale = mu * oneOverVoxelSize;
 
     float cz = mm.x;
@@ -1062,17 +1127,18 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
     float dn = 1.0f / sqrtf(rd.x * rd.x + rd.y * rd.y + rd.z * rd.z);
     rd.x *= dn, rd.y *= dn, rd.z *= dn;
 
-    float3 pt = ps;
-    VoxelCache cache = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1};
-    float sdf = 1.0f, conf = 0.0f, stepLength;
+    pt = ps;
+    VoxelCache cache = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0u};
+    float sdf = 1.0f, stepLength;
+    conf = 0.0f;
     int vm;
-    int nSteps = 0, nMiss = 0, nInterp = 0, nBlock = 0;
+    cnt.nSteps = cnt.nMiss = cnt.nInterp = cnt.nBlock = 0;
     bool hitSlot0 = false;
     while (totalLength < totalLengthMax)
     {
         sdf = sdf_uninterp(vba, table, pt, vm, cache);
         if (STATS)
-            nSteps++, nMiss += (vm == 0), nBlock += (vm > 1);
+            cnt.nSteps++, cnt.nMiss += (vm == 0), cnt.nBlock += (vm > 1);
         if (modifyVisible)
         {
             // NB: a cache hit reports vm == 1, i.e. slot 0 -- reference quirk kept (Access.h:86-90).  Nearly every step of every ray is
@@ -1080,7 +1146,7 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
             // (the L2 slice owning that sector serialised them and every load behind them waited: 5x the long-scoreboard stall of the
             // free-view variant)
             if (vm > 1)
-                visType[vm - 1] = 1;
+                mark(vm - 1);
             else if (vm == 1)
                 hitSlot0 = true;
         }
@@ -1089,7 +1155,7 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
         else
         {
             if (STATS)
-                nInterp += ((sdf <= 0.1f) && (sdf >= -0.5f));
+                cnt.nInterp += ((sdf <= 0.1f) && (sdf >= -0.5f));
             if ((sdf <= 0.1f) && (sdf >= -0.5f))
                 sdf = sdf_interp<false>(vba, table, pt, vm, cache, conf);
             if (sdf <= 0.0f)
@@ -1103,9 +1169,8 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
     {
         const unsigned act = __activemask();
         if (__any_sync(act, hitSlot0) && lane == __ffs(act) - 1)
-            visType[0] = 1;
+            mark(0);
     }
-    bool found;
     if (sdf <= 0.0f)
     {
         stepLength = sdf * stepScale;
@@ -1113,20 +1178,44 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
         sdf = sdf_interp<true>(vba, table, pt, vm, cache, conf);
         stepLength = sdf * stepScale;
         pt.x += stepLength * rd.x, pt.y += stepLength * rd.y, pt.z += stepLength * rd.z;
-        found = true;
+        return true;
     }
-    else
-        found = false;
+    return false;
+}
+
+// STATS (diagnostic build of the same loop, gsb_tsdf_raycast_stats): visType is reinterpreted as unsigned long long[8] totals --
+// rays, march steps, steps in unallocated space, trilinear reads, steps that changed voxel block, warp-max steps summed over warps, warps
+template <bool modifyVisible, bool withColour, bool STATS = false>
+__global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay, uchar4 *__restrict__ colourOut, unsigned char *visType,
+                                                  const Voxel *__restrict__ vbaPtr, const HashEntry *__restrict__ table, int W, int H, Mat4 invM,
+                                                  float4 invProj /* 1/fx 1/fy -cx -cy */, float oneOverVoxelSize, float mu,
+                                                  const float2 *__restrict__ minmax, int mmW)
+{
+    // 32x8 pixel tile per CTA, one 8x4 pixel patch per warp: the 32 rays of a warp share one cell of the 1/8-resolution range
+    // image and march through the same few voxel blocks, so they take nearly the same number of steps (a warp runs for as long
+    // as its slowest ray) and their hash / voxel reads hit the same lines; each patch row is still one 128-byte store.
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
+    int y = blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
+    if (x >= W || y >= H)
+        return;
+    float2 mm = __ldg(&minmax[(x >> 3) + (y >> 3) * mmW]);
+    const VbaLocal vba = {vbaPtr};
+    const MarkLocal mark = {visType};
+    float3 pt;
+    float conf;
+    RayCounters cnt;
+    const bool found = cast_ray<modifyVisible, STATS>(vba, table, mark, x, y, invM, invProj, oneOverVoxelSize, mu, mm, pt, conf, cnt);
     int loc = x + y * W;
     if (STATS)
     {
         unsigned long long *tot = reinterpret_cast<unsigned long long *>(visType);
         const unsigned act = __activemask();
-        int warpMax = nSteps;
+        int warpMax = cnt.nSteps;
         for (int o = 16; o; o >>= 1)
             warpMax = max(warpMax, __shfl_xor_sync(act, warpMax, o));
-        atomicAdd(tot + 0, 1ull), atomicAdd(tot + 1, (unsigned long long)nSteps), atomicAdd(tot + 2, (unsigned long long)nMiss);
-        atomicAdd(tot + 3, (unsigned long long)nInterp), atomicAdd(tot + 4, (unsigned long long)nBlock);
+        atomicAdd(tot + 0, 1ull), atomicAdd(tot + 1, (unsigned long long)cnt.nSteps), atomicAdd(tot + 2, (unsigned long long)cnt.nMiss);
+        atomicAdd(tot + 3, (unsigned long long)cnt.nInterp), atomicAdd(tot + 4, (unsigned long long)cnt.nBlock);
         if (lane == __ffs(act) - 1)
             atomicAdd(tot + 5, (unsigned long long)warpMax), atomicAdd(tot + 6, 1ull);
         return;
@@ -1142,16 +1231,92 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
     }
 }
 
+// Sharded raycast (world > 1): this rank marches the rays of its slab of rows [row0, row0 + 8 * gridDim.y); voxels are read from the rank that
+// owns their block (peer loads over NVLink -- the hash table is local).  LIVE: visibility marks go to every rank, the result stays local
+// except the two rows next to a slab border, which the neighbour's ICP-map kernel needs for its finite differences.  Free view: every
+// rank receives every row (the all-gather is the kernel's own output store), colour included.
+template <bool LIVE>
+__global__ void __launch_bounds__(256) k_raycast_sharded(const __grid_constant__ ShardView v, const HashEntry *__restrict__ table, int W, int H,
+                                                          int row0, int row1, Mat4 invM, float4 invProj, float oneOverVoxelSize, float mu,
+                                                          const float2 *__restrict__ minmax, int mmW)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
+    int y = row0 + blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
+    if (x >= W || y >= row1)
+        return;
+    float2 mm = __ldg(&minmax[(x >> 3) + (y >> 3) * mmW]);
+    const VbaSharded vba = {&v};
+    float3 pt;
+    float conf;
+    RayCounters cnt;
+    bool found;
+    if (LIVE)
+    {
+        const MarkAll mark = {&v};
+        found = cast_ray<true, false>(vba, table, mark, x, y, invM, invProj, oneOverVoxelSize, mu, mm, pt, conf, cnt);
+    }
+    else
+    {
+        const MarkNone mark;
+        found = cast_ray<false, false>(vba, table, mark, x, y, invM, invProj, oneOverVoxelSize, mu, mm, pt, conf, cnt);
+    }
+    const int loc = x + y * W;
+    const float4 out = make_float4(pt.x, pt.y, pt.z, found ? conf + 1.0f : 0.0f);
+    if (LIVE)
+    {
+        v.rayLive[v.rank][loc] = out;
+        if (v.rank > 0 && y < row0 + 2)
+            v.rayLive[v.rank - 1][loc] = out;
+        if (v.rank < v.world - 1 && y >= row1 - 2)
+            v.rayLive[v.rank + 1][loc] = out;
+    }
+    else
+    {
+        uchar4 col = make_uchar4(0, 0, 0, 0);
+        if (found && (conf + 1.0f) > 0)
+            col = colour_interp(vba, table, pt);
+        for (int q = 0; q < v.world; q++)
+        {
+            v.rayFree[q][loc] = out;
+            v.imageFree[q][loc] = col;
+        }
+    }
+}
+
+// Cross-GPU barrier of the sharded TSDF path: lane q signals rank q ("I have reached barrier `epoch`") and waits for rank q's signal;
+// release / acquire at system scope, bounded spin (a rank that never arrives becomes an error flag, not a hung GPU).
+__global__ void k_shard_barrier(const __grid_constant__ ShardView v, unsigned epoch, int *err)
+{
+    const int q = threadIdx.x;
+    if (q >= v.world)
+        return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(v.flags[q] + v.rank), "r"(epoch) : "memory");
+    const unsigned *mine = v.flags[v.rank] + q;
+    const long long t0 = clock64();
+    for (;;)
+    {
+        unsigned got;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+        if ((int)(got - epoch) >= 0)
+            break;
+        if (clock64() - t0 > 40000000000LL)
+        {
+            *err = 1;
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // B8: ICP maps.  reference: processPixelICP<true,false> (Visualisation_Shared.h:438-480),
 // computeNormalAndAngle<true,false> (:257-338)
-__global__ void __launch_bounds__(256) k_icp_maps(float4 *__restrict__ pointsMap, float4 *__restrict__ normalsMap,
-                                                   const float4 *__restrict__ pointsRay, int W, int H, float voxelSize, float3 light)
+__device__ __forceinline__ void icp_map_pixel(const float4 *__restrict__ pointsRay, int x, int y, int W, int H, float voxelSize, float3 light,
+                                              float4 &pm, float4 &nm)
 {
-    int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= H)
-        return;
     int loc = x + y * W;
     float4 point = __ldg(&pointsRay[loc]);
     bool found = point.w > 0.0f;
@@ -1201,14 +1366,51 @@ __global__ void __launch_bounds__(256) k_icp_maps(float4 *__restrict__ pointsMap
     }
     if (found)
     {
-        pointsMap[loc] = make_float4(point.x * voxelSize, point.y * voxelSize, point.z * voxelSize, point.w);
-        normalsMap[loc] = make_float4(n.x, n.y, n.z, 0.0f);
+        pm = make_float4(point.x * voxelSize, point.y * voxelSize, point.z * voxelSize, point.w);
+        nm = make_float4(n.x, n.y, n.z, 0.0f);
+    }
+    else
+        pm = nm = make_float4(0, 0, 0, -1.0f);
+}
+
+__global__ void __launch_bounds__(256) k_icp_maps(float4 *__restrict__ pointsMap, float4 *__restrict__ normalsMap,
+                                                   const float4 *__restrict__ pointsRay, int W, int H, float voxelSize, float3 light)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H)
+        return;
+    float4 pm, nm;
+    icp_map_pixel(pointsRay, x, y, W, H, voxelSize, light, pm, nm);
+    pointsMap[x + y * W] = pm;
+    normalsMap[x + y * W] = nm;
+}
+
+// sharded: the rows of this rank's slab (the raycast kernel has delivered the two neighbour rows on either side); with PUSH_ALL (tracking on:
+// the ICP of the next frame projects into the whole maps) every rank receives every row
+template <bool PUSH_ALL>
+__global__ void __launch_bounds__(256) k_icp_maps_sharded(const __grid_constant__ ShardView v, int W, int H, int row0, int row1, float voxelSize,
+                                                           float3 light)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    int y = row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= row1)
+        return;
+    float4 pm, nm;
+    icp_map_pixel(v.rayLive[v.rank], x, y, W, H, voxelSize, light, pm, nm);
+    const int loc = x + y * W;
+    if (PUSH_ALL)
+    {
+        for (int q = 0; q < v.world; q++)
+        {
+            v.pointsMap[q][loc] = pm;
+            v.normalsMap[q][loc] = nm;
+        }
     }
     else
     {
-        float4 o = make_float4(0, 0, 0, -1.0f);
-        pointsMap[loc] = o;
-        normalsMap[loc] = o;
+        v.pointsMap[v.rank][loc] = pm;
+        v.normalsMap[v.rank][loc] = nm;
     }
 }
 
@@ -1264,8 +1466,10 @@ void allocate(const Scene &s, const Frame &f, const Camera &cam, cudaStream_t st
     k_alloc_apply<<<nChunks, SCAN_CTA, 0, st>>>(s.allocKey, s.table, s.visType, s.E, nChunks, s.chunkCounts, s.state, s.state, f.depth_f, f.W,
                                                 cam.invM, invProj, s.mu, oneOverBlock);
     float4 proj = make_float4(cam.fx, cam.fy, cam.cx, cam.cy);
-    k_visible_count<<<nChunks, SCAN_CTA, 0, st>>>(s.visType, s.table, s.E, cam.M, proj, s.voxelSize, f.W, f.H, s.chunkCounts, s.state);
-    k_visible_compact<<<nChunks, SCAN_CTA, 0, st>>>(s.visType, s.E, nChunks, s.chunkCounts, s.visIds, s.numBlocks, s.state + 2);
+    k_visible_count<<<nChunks, SCAN_CTA, 0, st>>>(s.visType, s.table, s.E, cam.M, proj, s.voxelSize, f.W, f.H, s.chunkCounts, s.state, s.rank,
+                                                  s.world);
+    k_visible_compact<<<nChunks, SCAN_CTA, 0, st>>>(s.visType, s.E, nChunks, s.chunkCounts, s.visIds, s.numBlocks, s.state + 2, s.table, s.rank,
+                                                    s.world, s.visIdsOwn, s.state + 6);
 }
 
 void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, cudaStream_t st)
@@ -1275,12 +1479,15 @@ void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, c
     P.proj = make_float4(cam.fx, cam.fy, cam.cx, cam.cy);
     P.mu = s.mu, P.voxelSize = s.voxelSize, P.maxW = s.maxW, P.W = f.W, P.H = f.H;
     GS_COUNT_LAUNCHES(1);
+    // sharded scene: only the visible blocks this rank owns (per-block independent work, no exchange)
+    const int *ids = s.world > 1 ? s.visIdsOwn : s.visIds;
+    const int *nIds = s.world > 1 ? s.state + 6 : s.state + 2;
     if (variant == 1)
-        k_integrate_direct<<<148 * 4, 512, 0, st>>>(s.vba, s.table, s.visIds, s.state + 2, P, f.depth_f, f.rgba);
+        k_integrate_direct<<<148 * 4, 512, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
     else if (variant == 2)
-        k_integrate_ws<<<148 * 4, WS_THREADS, 0, st>>>(s.vba, s.table, s.visIds, s.state + 2, P, f.depth_f, f.rgba);
+        k_integrate_ws<<<148 * 4, WS_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
     else
-        k_integrate_tma<<<148 * 5, INT_THREADS, 0, st>>>(s.vba, s.table, s.visIds, s.state + 2, P, f.depth_f, f.rgba);
+        k_integrate_tma<<<148 * 5, INT_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
 }
 
 void expected_depth_live(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st)
@@ -1319,6 +1526,44 @@ void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minm
     else
         k_raycast<false, false><<<grid, 256, 0, st>>>(pointsRay, nullptr, nullptr, s.vba, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax,
                                                       mmW);
+}
+
+void raycast_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, const float2 *minmax, bool live, cudaStream_t st)
+{
+    int y0, y1;
+    slab_rows(H, v.rank, v.world, y0, y1);
+    if (y1 <= y0)
+        return;
+    dim3 grid(cdiv(W, 32), cdiv(y1 - y0, 8));
+    float4 invProj = make_float4(1.0f / cam.fx, 1.0f / cam.fy, -cam.cx, -cam.cy);
+    float oneOverVoxel = 1.0f / s.voxelSize;
+    int mmW = cdiv(W, 8);
+    GS_COUNT_LAUNCHES(1);
+    if (live)
+        k_raycast_sharded<true><<<grid, 256, 0, st>>>(v, s.table, W, H, y0, y1, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
+    else
+        k_raycast_sharded<false><<<grid, 256, 0, st>>>(v, s.table, W, H, y0, y1, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
+}
+
+void icp_maps_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, bool pushAll, cudaStream_t st)
+{
+    int y0, y1;
+    slab_rows(H, v.rank, v.world, y0, y1);
+    if (y1 <= y0)
+        return;
+    dim3 grid(cdiv(W, 32), cdiv(y1 - y0, 8));
+    float3 light = make_float3(-cam.invM.m[8], -cam.invM.m[9], -cam.invM.m[10]);
+    GS_COUNT_LAUNCHES(1);
+    if (pushAll)
+        k_icp_maps_sharded<true><<<grid, 256, 0, st>>>(v, W, H, y0, y1, s.voxelSize, light);
+    else
+        k_icp_maps_sharded<false><<<grid, 256, 0, st>>>(v, W, H, y0, y1, s.voxelSize, light);
+}
+
+void shard_barrier(const ShardView &v, unsigned epoch, int *errFlag, cudaStream_t st)
+{
+    GS_COUNT_LAUNCHES(1);
+    k_shard_barrier<<<1, 32, 0, st>>>(v, epoch, errFlag);
 }
 
 // diagnostic: the free-view march with step counters instead of outputs; totals8 = device unsigned long long[8], zeroed by the caller

@@ -72,6 +72,12 @@ def load_library():
     L.gsb_tsdf_create.argtypes = [C.POINTER(TsdfConfig), C.POINTER(C.c_void_p)]
     L.gsb_tsdf_destroy.argtypes = [C.c_void_p]
     L.gsb_tsdf_destroy.restype = None
+    L.gsb_tsdf_create_sharded.argtypes = [C.POINTER(TsdfConfig), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.gsb_tsdf_shard_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.gsb_tsdf_shard_attach.argtypes = [C.c_void_p, C.c_void_p]
+    L.gsb_tsdf_shard_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.gsb_tsdf_shard_error.argtypes = [C.c_void_p]
+    L.gsb_tsdf_shard_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     L.gsb_tsdf_reset.argtypes = [C.c_void_p]
     L.gsb_tsdf_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.gsb_tsdf_get_stream.argtypes = [C.c_void_p]
@@ -167,7 +173,9 @@ def _ptr(x):
 
 class TsdfEngine:
     def __init__(self, intr, voxel_size=0.005, mu=0.02, view_frustum_min=0.2, view_frustum_max=10.0,
-                 tracker=0, device=0, num_blocks=0, integrate_variant=0, max_w=100):
+                 tracker=0, device=0, num_blocks=0, integrate_variant=0, max_w=100, rank=0, world=1):
+        """world > 1: the voxel hash is sharded by spatial block over `world` engines (gsb_tsdf_create_sharded); map the peers with
+        export_handle() / attach(handles) between processes or attach_local(engines) inside one process before the first frame."""
         L = load_library()
         self.L = L
         cfg = TsdfConfig()
@@ -183,14 +191,39 @@ class TsdfEngine:
         self.w, self.h = cfg.width, cfg.height
         self.num_blocks = cfg.num_blocks
         self.E = 0x100000 + 0x20000
+        self.rank, self.world = rank, world
         h = C.c_void_p()
-        _check(L.gsb_tsdf_create(C.byref(cfg), C.byref(h)))
+        _check(L.gsb_tsdf_create_sharded(C.byref(cfg), rank, world, C.byref(h)))
         self.h_ = h
 
     def close(self):
         if getattr(self, "h_", None):
             self.L.gsb_tsdf_destroy(self.h_)
             self.h_ = None
+
+    # ---- sharded scene ----
+    def export_handle(self):
+        buf = C.create_string_buffer(64)
+        _check(self.L.gsb_tsdf_shard_export(self.h_, buf))
+        return buf.raw
+
+    def attach(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        _check(self.L.gsb_tsdf_shard_attach(self.h_, C.c_char_p(blob)))
+
+    def attach_local(self, engines):
+        arr = (C.c_void_p * self.world)(*[e.h_ for e in engines])
+        _check(self.L.gsb_tsdf_shard_attach_local(self.h_, arr))
+
+    def shard_error(self):
+        return int(self.L.gsb_tsdf_shard_error(self.h_))
+
+    def shard_rows(self):
+        """image rows [row0, row1) this rank raycasts"""
+        r0, r1 = C.c_int(), C.c_int()
+        _check(self.L.gsb_tsdf_shard_info(self.h_, None, None, C.byref(r0), C.byref(r1)))
+        return r0.value, r1.value
 
     __del__ = close
 

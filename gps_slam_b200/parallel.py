@@ -37,6 +37,27 @@ def owner_of(points, world):
     return (_hash_u32(h) % np.uint64(max(world, 1))).astype(np.int64)
 
 
+def voxel_block_owner(block_pos, world):
+    """rank that owns the voxel data of each TSDF block [N,3] (integer block coordinates): hashIndex(blockPos) mod world, the
+    reference's own hash (ITMRepresentationAccess.h:7-11) -- host mirror of tsdf::block_owner (csrc/tsdf.h)"""
+    b = np.asarray(block_pos).astype(np.int64)
+    h = ((b[:, 0] * 73856093) & 0xffffffff) ^ ((b[:, 1] * 19349669) & 0xffffffff) ^ ((b[:, 2] * 83492791) & 0xffffffff)
+    return ((h & 0xfffff) % max(world, 1)).astype(np.int64)
+
+
+def make_sharded_tsdf(intr, rank, world, device, **kw):
+    """TsdfEngine whose voxel hash is sharded over `world` ranks (one process per GPU): the 64-byte CUDA IPC handles of the shared
+    segments travel once through torch.distributed; afterwards the TSDF path uses peer memory only (no collective library)"""
+    from . import engine as E
+    eng = E.TsdfEngine(intr, device=device, rank=rank, world=world, **kw)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.export_handle())
+        eng.attach(handles)
+        dist.barrier()
+    return eng
+
+
 def shard_params(params, rank, world):
     """keep the rows of a parameter dict (means, scales, ...) owned by `rank`"""
     if world <= 1:

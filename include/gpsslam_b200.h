@@ -57,6 +57,23 @@ typedef struct gsb_tsdf_config
 
 void gsb_tsdf_default_config(gsb_tsdf_config_t *cfg);
 int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out);
+/* Voxel hash sharded by spatial block over `world` GPUs of one box (one engine per GPU, one process per GPU or several engines in one
+ * process).  The hash table, allocation and visibility lists are computed identically by every rank (every rank is given
+ * every frame); the voxel DATA of a block lives on rank hashIndex(blockPos) mod world only (reference hash: ITMRepresentationAccess.h:7-11).
+ * ProcessFrame integrates the visible blocks this rank owns (per-block independent, ITMSceneReconstructionEngine_CUDA.tcu:348-383);
+ * raycasts are split by image rows, read the voxels from their owner over NVLink peer memory (castRay, ITMVisualisationEngine_Shared.h:
+ * 122-221) and store their rows straight into the other ranks' images; cross-GPU ordering is two flag barriers per frame through peer
+ * memory.  Every rank must issue the same sequence of process_frame / run_raycast calls.  Results are bit-identical to world == 1:
+ * hash table, visible list, poses, free-view vertex / colour images on EVERY rank; GSB_TSDF_VOXELS holds the blocks this rank owns;
+ * live raycast and ICP maps hold this rank's rows (gsb_tsdf_shard_info) unless tracking is on (then every rank holds all rows of the maps).
+ * After create_sharded the peers' segments must be mapped once: between processes exchange the 64-byte handles of shard_export (any
+ * transport) and call shard_attach(handles of all ranks in rank order); engines inside one process use shard_attach_local. */
+int gsb_tsdf_create_sharded(const gsb_tsdf_config_t *cfg, int rank, int world, gsb_tsdf_t **out);
+int gsb_tsdf_shard_export(gsb_tsdf_t *e, void *handle64);
+int gsb_tsdf_shard_attach(gsb_tsdf_t *e, const void *handles /* world x 64 bytes */);
+int gsb_tsdf_shard_attach_local(gsb_tsdf_t *e, gsb_tsdf_t *const *peers /* world engines in rank order */);
+int gsb_tsdf_shard_error(gsb_tsdf_t *e);   /* non-zero: a cross-GPU barrier or exchange timed out (a peer never arrived) */
+int gsb_tsdf_shard_info(gsb_tsdf_t *e, int *rank, int *world, int *row0, int *row1);   /* image rows [row0, row1) this rank raycasts */
 void gsb_tsdf_destroy(gsb_tsdf_t *e);
 int gsb_tsdf_reset(gsb_tsdf_t *e);                               /* ITMBasicEngine::resetAll */
 int gsb_tsdf_set_stream(gsb_tsdf_t *e, void *cuda_stream);       /* cudaStream_t; NULL = private stream */
@@ -111,7 +128,8 @@ enum
     GSB_TSDF_IMAGE_FREE = 11     /* uchar4[h*w]                                           */
 };
 int gsb_tsdf_read(gsb_tsdf_t *e, int what, void *dst_host, size_t bytes);
-/* which: 0 lastFreeBlockId, 1 lastFreeExcessListId, 2 noVisibleEntries, 3 error flag (synchronises) */
+/* which: 0 lastFreeBlockId, 1 lastFreeExcessListId, 2 noVisibleEntries, 3 error flag, 6 visible entries owned by this rank (sharded scene);
+ * synchronises */
 int gsb_tsdf_counter(gsb_tsdf_t *e, int which, int *value);
 
 /* ITMBasicEngine::LoadFromFile (Core/ITMBasicEngine.tpp:137-171) minus the file I/O: resets the engine, then installs the scene from
