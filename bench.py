@@ -446,7 +446,7 @@ def main():
                             "parallelism": pipe.parallelism(), "frames_per_step": FRAMES_PER_STEP, "width": intr["width"], "height": intr["height"],
                             "l2": "no explicit flush: every frame is new input (4.9 MB) and each step streams the visible voxel "
                                   "blocks 10x (V x 8 KB per frame), working set > 126 MB L2", "quality": psnr, "ms_per_step_each": per_step_ms,
-                            "full_run": full_run, "tracking": tracking}, **stats_window),
+                            "full_run": full_run, "tracking": tracking, "breakdown": (roofline or {}).get("step_breakdown")}, **stats_window),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pinned host frames through gsb_tsdf_process_frame (H2D per frame); D2H once per 10-frame step: the pose estimate "

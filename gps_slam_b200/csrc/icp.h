@@ -17,6 +17,9 @@ void convert_depth(const short *depth_mm, float *depth_f, int W, int H, cudaStre
 // TrackCamera: updates *pose_d in place (host pose, final value read back once per frame)
 int track_camera(Tracker *t, const float *depth_f, const float4 *pointsMap, const float4 *normalsMap, float fx, float fy, float cx, float cy,
                  const Mat4 &scenePose, int trackingFrames, se3::Pose *pose_d, cudaStream_t st);
+// ICP sharded over `world` GPUs (row split + in-kernel all-reduce of the 29 sums through peer memory): xchg[q] = rank q's exchange block
+// ([2][16][32] floats, zero-initialised, peer-mapped), err = host-mapped flag raised when a peer does not deliver
+void set_shard(Tracker *t, int rank, int world, float *const *xchg, int *err);
 // single evaluation at one pyramid level for a given camera->world estimate (ComputeGandH_Depth / ComputeGandH), for parity tests
 int icp_eval(Tracker *t, const float *depth_f, const float4 *pointsMap, const float4 *normalsMap, float fx, float fy, float cx, float cy,
              const Mat4 &scenePose, int trackingFrames, int level, const Mat4 &approxInvPose, int *nValid, float *f, float *nabla6, float *hessian36,

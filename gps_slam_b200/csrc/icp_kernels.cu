@@ -17,6 +17,7 @@
 //    tracker are not built because only level 0 of the scene hierarchy is ever read (ITMExtendedTracker.cpp:297).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -59,6 +60,13 @@ struct Params
     float vfmin, vfmax, tukeyCutOff;
     int framesToSkip, framesToWeight, useWeights;
     float terminationThreshold;
+    // ICP sharded over the GPUs of a box: this rank accumulates rows [h * rank / world, h * (rank + 1) / world) of every
+    // level; the 29 sums are exchanged through peer memory inside the persistent kernel, every rank adds the world partial sums in rank
+    // order and takes the identical LM step.  xchg[q] = rank q's exchange block [2][16][32] floats (slot 31 of a row = sequence stamp).
+    int rank, world;
+    float *xchg[16];
+    unsigned xseqBase;   // exchanges completed by earlier launches (identical on every rank)
+    int *err;            // host-mapped flag: a peer did not deliver within the spin bound
 };
 
 // device-resident tracker state; the host reads it back once per frame
@@ -98,6 +106,11 @@ struct Tracker
     float *hk_table;
     int lastResult;
     float lastScore;
+    // sharded ICP (set_shard): peers' exchange blocks, exchanges done so far, error flag
+    int rank, world;
+    float *xchg[16];
+    unsigned xseq;
+    int *err;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -230,8 +243,8 @@ __device__ __forceinline__ void accumulate(const Params &P, const Level &L, cons
     const int type = L.type;
     const int off = (type == IT_TRANSLATION) ? 3 : 0;   // which half of A is active for short iterations
     const int noPara = (type == IT_BOTH) ? 6 : 3;
-    const int n = L.w * L.h;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    const int iBegin = (int)((long long)L.h * P.rank / P.world) * L.w, iEnd = (int)((long long)L.h * (P.rank + 1) / P.world) * L.w;
+    for (int i = iBegin + blockIdx.x * blockDim.x + threadIdx.x; i < iEnd; i += gridDim.x * blockDim.x)
     {
         int y = i / L.w, x = i - y * L.w;
         float A6[6], b, wgt;
@@ -491,12 +504,57 @@ __global__ void __launch_bounds__(CTA) k_icp_track(Params P, State *state, float
             grid_sync(barrier, nb);
             if (blockIdx.x == 0)
             {
+                float s = 0.f;
                 if (threadIdx.x < NACC)
                 {
-                    float s = 0.f;
                     for (unsigned b = 0; b < nb; b++)
                         s += __ldcg(&partials[(size_t)b * NACC + threadIdx.x]);
                     sfinal[threadIdx.x] = s;
+                }
+                if (P.world > 1)
+                {
+                    // one-shot all-reduce of the 29 sums through peer memory: store my partial sums into row `rank` of every rank's
+                    // exchange block (double-buffered by sequence parity: a fast rank is at most one exchange ahead), stamp the rows,
+                    // wait for every rank's stamp in my own block, add the rows in rank order
+                    const unsigned seq = P.xseqBase + (unsigned)__ldcg(&state->iterationsRun) + 1u;
+                    const int buf = (int)(seq & 1u);
+                    if (threadIdx.x < NACC)
+                        for (int q = 0; q < P.world; q++)
+                            P.xchg[q][(buf * 16 + P.rank) * 32 + threadIdx.x] = s;
+                    __threadfence_system();
+                    __syncthreads();
+                    if (threadIdx.x < P.world)
+                    {
+                        const int q = threadIdx.x;
+                        unsigned *stamp = reinterpret_cast<unsigned *>(P.xchg[q] + (buf * 16 + P.rank) * 32 + 31);
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(stamp), "r"(seq) : "memory");
+                        const unsigned *mine = reinterpret_cast<const unsigned *>(P.xchg[P.rank] + (buf * 16 + q) * 32 + 31);
+                        const long long t0 = clock64();
+                        for (;;)
+                        {
+                            unsigned got;
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+                            if (got == seq)
+                                break;
+                            if (clock64() - t0 > 40000000000LL)
+                            {
+                                *P.err = 1;
+                                break;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < NACC)
+                    {
+                        float tot = 0.f;
+                        for (int q = 0; q < P.world; q++)
+                        {
+                            float part;
+                            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(part) : "l"(P.xchg[P.rank] + (buf * 16 + q) * 32 + threadIdx.x) : "memory");
+                            tot += part;
+                        }
+                        sfinal[threadIdx.x] = tot;
+                    }
                 }
                 __syncthreads();
                 if (threadIdx.x == 0)
@@ -668,6 +726,10 @@ Tracker *create_tracker(int kind, int W, int H, float vfmin, float vfmax)
         perSm = 1;
     if (perSm > 2)
         perSm = 2;
+    // tests that run several sharded engines on ONE device: their persistent kernels wait for each other, so all of them must be
+    // co-resident (one process per GPU -- the product layout -- has the device to itself)
+    if (const char *v = getenv("GSB_ICP_CTAS_PER_SM"))
+        perSm = atoi(v) >= 1 ? (atoi(v) < perSm ? atoi(v) : perSm) : perSm;
     t->grid = sms * perSm;
     ok = ok && cudaMalloc((void **)&t->partials, sizeof(float) * NACC * (size_t)t->grid) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&t->barrier, sizeof(unsigned)) == cudaSuccess;
@@ -732,6 +794,11 @@ static void fill_params(Tracker *t, Params &P, const float *depth_f, const float
     P.framesToSkip = 20, P.framesToWeight = 50;
     P.useWeights = (t->kind == 1 && trackingFrames >= 100) ? 1 : 0; // ITMExtendedTracker_CUDA.cu:141
     P.terminationThreshold = t->kind == 1 ? 1e-4f : 1e-3f;
+    P.rank = t->rank, P.world = t->world > 0 ? t->world : 1;
+    for (int q = 0; q < 16; q++)
+        P.xchg[q] = t->xchg[q];
+    P.xseqBase = t->xseq;
+    P.err = t->err;
     int w = t->W, h = t->H;
     float4 intr = make_float4(fx, fy, cx, cy);
     const float *prev = depth_f;
@@ -817,8 +884,28 @@ int track_camera(Tracker *t, const float *depth_f, const float4 *pointsMap, cons
     GS_CUDA_OK(cudaMemcpyAsync(&hs, t->state, sizeof(State), cudaMemcpyDeviceToHost, st));
     GS_CUDA_OK(cudaStreamSynchronize(st));
     *pose_d = hs.pose_d;
+    t->xseq += (unsigned)hs.iterationsRun;   // one exchange per LM iteration; the same count on every rank
     update_pose_quality(t, hs, t->thresh[0]);
     return 0;
+}
+
+void set_shard(Tracker *t, int rank, int world, float *const *xchg, int *err)
+{
+    t->rank = rank, t->world = world, t->err = err, t->xseq = 0;
+    // The persistent kernel now waits for other GPUs in the middle of its run, and those GPUs may be waiting for THIS GPU's Gaussian stream
+    // (exchange barriers of the optimiser iterations): the tracker must not occupy the device exclusively, or the two waits close a cycle.
+    // One CTA per SM (half the register file) leaves room for the other stream's kernels to run beside it; each rank only accumulates
+    // 1 / world of the pixels, so the smaller grid costs nothing.
+    if (world > 1)
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (t->grid > sms)
+            t->grid = sms;
+    }
+    for (int q = 0; q < 16; q++)
+        t->xchg[q] = q < world ? xchg[q] : nullptr;
 }
 
 int icp_eval(Tracker *t, const float *depth_f, const float4 *pointsMap, const float4 *normalsMap, float fx, float fy, float cx, float cy,
@@ -829,6 +916,7 @@ int icp_eval(Tracker *t, const float *depth_f, const float4 *pointsMap, const fl
         return gs_set_error(__FILE__, __LINE__, "bad pyramid level");
     Params P;
     fill_params(t, P, depth_f, pointsMap, normalsMap, fx, fy, cx, cy, scenePose, trackingFrames, st);
+    P.rank = 0, P.world = 1;   // a local evaluation over the whole image (the maps are complete on every rank while tracking is on)
     Mat4 pose = approxInvPose;
     void *args[] = {(void *)&P, (void *)&level, (void *)&pose, (void *)&t->state, (void *)&t->partials, (void *)&t->barrier};
     GS_COUNT_LAUNCHES(1);

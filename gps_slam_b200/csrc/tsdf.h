@@ -23,14 +23,25 @@ struct Scene
     // the same), the voxel DATA of a block lives on one rank only: owner = hashIndex(blockPos) mod world.
     int rank, world;
     int *visIdsOwn;          // [numBlocks]  the visible entries this rank owns (ascending); == visIds for world == 1
+    // shard mode 1 ("owner computes, everybody stores"): the integrate kernel writes every block it has updated into the other ranks'
+    // voxel block arrays as well (TMA bulk stores over NVLink), so every rank keeps a complete copy and raycasts read local memory
+    int nPush;
+    Voxel *pushVba[15];
 };
 
 constexpr int SHARD_MAX_WORLD = 16;
+struct PeerVbas
+{
+    int n;
+    Voxel *p[SHARD_MAX_WORLD - 1];
+};
 
 // what the sharded kernels see of the other ranks (peer-mapped device pointers, index = rank; own entry = local buffer)
 struct ShardView
 {
     int rank, world;
+    int replicated;          // shard mode 1: voxel reads are local (vba[rank] is complete)
+    int probe;               // measurement aid (gsb_tsdf_shard_probe): 1 = results stay local (no peer stores), 2 = per-thread peer stores
     const Voxel *vba[SHARD_MAX_WORLD];
     unsigned char *visType[SHARD_MAX_WORLD];
     float4 *rayLive[SHARD_MAX_WORLD];
@@ -46,7 +57,8 @@ __host__ __device__ inline int block_owner(int bx, int by, int bz, int world)
 {
     return (int)((((unsigned)bx * 73856093u) ^ ((unsigned)by * 19349669u) ^ ((unsigned)bz * 83492791u)) & (unsigned)SDF_HASH_MASK) % world;
 }
-// rows [y0, y1) of the image a rank raycasts: contiguous slabs of whole 8-row tiles
+// rows [y0, y1) of the ICP maps a rank computes: contiguous slabs of whole 8-row tiles (the raycast itself is dealt in interleaved
+// 8-row strips, strip t to rank t mod world)
 __host__ __device__ inline void slab_rows(int H, int rank, int world, int &y0, int &y1)
 {
     const int tiles = (H + 7) / 8;
@@ -79,8 +91,8 @@ void raycast_stats(const Scene &s, const Camera &cam, int W, int H, const float2
 void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minmax, float4 *pointsRay, uchar4 *colour, bool modifyVisible,
              cudaStream_t st);
 void icp_maps(const Scene &s, const Camera &cam, int W, int H, const float4 *pointsRay, float4 *pointsMap, float4 *normalsMap, cudaStream_t st);
-// sharded forms (world > 1): this rank's slab of rows, voxels read from their owner's memory over NVLink; results are stored into
-// every rank's images (free view), resp. the two border rows into the neighbour slabs (live); visibility marks go to every rank
+// sharded forms (world > 1): this rank's share of the rows, voxels read from their owner's memory over NVLink (mode 0) or from the local
+// copy (mode 1); results are stored into every rank's images; the visibility marks of the live raycast go to every rank
 void raycast_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, const float2 *minmax, bool live, cudaStream_t st);
 void icp_maps_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, bool pushAll, cudaStream_t st);
 void shard_barrier(const ShardView &v, unsigned epoch, int *errFlag, cudaStream_t st);

@@ -65,6 +65,8 @@ struct gsb_tsdf
     unsigned epoch;      // barriers issued so far (identical on every rank: SPMD call sequence)
     int *errHost;        // pinned, mapped: set by a barrier (or an in-kernel exchange) that timed out
     tsdf::ShardView view;
+    int shardMode;       // 0: a block's voxels live on its owner only, raycasts read them over NVLink; 1: the owner integrates and stores the
+                         // block into every rank, raycasts read local memory
 };
 
 #define E_CUDA(call) GS_CUDA_OK(call)
@@ -96,6 +98,12 @@ static void fill_shard_view(gsb_tsdf *e)
 {
     tsdf::ShardView &v = e->view;
     v.rank = e->rank, v.world = e->world;
+    v.replicated = e->shardMode == 1;
+    v.probe = 0;
+    e->scene.nPush = 0;
+    for (int q = 0; q < e->world; q++)
+        if (e->shardMode == 1 && q != e->rank)
+            e->scene.pushVba[e->scene.nPush++] = (Voxel *)(e->peer[q] + e->offVba);
     for (int q = 0; q < e->world; q++)
     {
         char *b = e->peer[q];
@@ -153,6 +161,12 @@ extern "C" int gsb_tsdf_create_sharded(const gsb_tsdf_config_t *cfg, int rank, i
     }
     const int W = cfg->width, H = cfg->height, P = W * H;
     e->rank = rank, e->world = world;
+    // default: mode 1 (owner integrates, every rank stores; local raycast reads) -- measured on 2 and 8 B200s it is the faster of the two
+    // (profiles/r02_shard_modes.md); mode 0 keeps 1 / world of the voxel memory per GPU
+    e->shardMode = 1;
+    if (const char *v = getenv("GSB_TSDF_SHARD_MODE"))
+        e->shardMode = atoi(v) == 0 ? 0 : 1;
+    e->scene.nPush = 0;
     e->seg = nullptr, e->errHost = nullptr, e->epoch = 0, e->attached = world == 1;
     memset(e->peer, 0, sizeof e->peer);
     memset(e->ipcOpened, 0, sizeof e->ipcOpened);
@@ -292,6 +306,8 @@ extern "C" int gsb_tsdf_shard_attach(gsb_tsdf_t *e, const void *handles)
     }
     fill_shard_view(e);
     e->attached = true;
+    if (e->tracker)
+        icp::set_shard(e->tracker, e->rank, e->world, e->view.icpXchg, e->errHost);
     return 0;
 }
 
@@ -319,6 +335,29 @@ extern "C" int gsb_tsdf_shard_attach_local(gsb_tsdf_t *e, gsb_tsdf_t *const *pee
     }
     fill_shard_view(e);
     e->attached = true;
+    if (e->tracker)
+        icp::set_shard(e->tracker, e->rank, e->world, e->view.icpXchg, e->errHost);
+    return 0;
+}
+
+extern "C" int gsb_tsdf_shard_set_mode(gsb_tsdf_t *e, int mode)
+{
+    if (!e || e->world < 2 || (mode != 0 && mode != 1))
+        return gs_set_error(__FILE__, __LINE__, "not a sharded engine, or mode not 0 / 1");
+    if (e->framesProcessed != 0)
+        return gs_set_error(__FILE__, __LINE__, "the shard mode can only change on an empty scene");
+    e->shardMode = mode;
+    if (e->attached)
+        fill_shard_view(e);
+    return 0;
+}
+
+// measurement aid (tools/shard_probe.py): 0 normal, 1 = raycast results stay on this rank, 2 = per-thread instead of bulk peer stores
+extern "C" int gsb_tsdf_shard_probe(gsb_tsdf_t *e, int what)
+{
+    if (!e || e->world < 2)
+        return gs_set_error(__FILE__, __LINE__, "not a sharded engine");
+    e->view.probe = what;
     return 0;
 }
 
@@ -339,6 +378,7 @@ extern "C" int gsb_tsdf_shard_info(gsb_tsdf_t *e, int *rank, int *world, int *ro
 
 extern "C" int gsb_tsdf_reset(gsb_tsdf_t *e)
 {
+    E_CUDA(cudaSetDevice(e->cfg.device));
     tsdf::reset_scene(e->scene, e->stream);
     const int W = e->cfg.width, H = e->cfg.height, P = W * H;
     E_CUDA(cudaMemsetAsync(e->rayLive, 0, sizeof(float4) * P, e->stream));
@@ -419,6 +459,7 @@ static int process_resident(gsb_tsdf *e, const float *gt_c2w)
     cudaStream_t st = e->stream;
     if (!e->attached)
         return gs_set_error(__FILE__, __LINE__, "sharded engine: the peer segments are not attached (gsb_tsdf_shard_attach)");
+    E_CUDA(cudaSetDevice(e->cfg.device));   // several engines of one process may sit on different devices
     auto mark = [&](int i)
     {
         if (e->stageTiming)
@@ -474,9 +515,9 @@ static int process_resident(gsb_tsdf *e, const float *gt_c2w)
     else
     {
         // Sharded scene.  Barrier A: every rank has integrated its blocks of this frame (and has finished reading what the raycast is
-        // about to overwrite).  The raycast reads the other ranks' voxels, stores its visibility marks into every rank and its border
-        // rows into the neighbour slabs.  Barrier B: all of that has landed, nobody reads voxels any more -> the next frame may
-        // integrate; the ICP maps of the slab follow (every rank receives every row while tracking is on, then barrier C).
+        // about to overwrite).  The raycast reads the other ranks' voxels (mode 0), stores its visibility marks and its rows into every
+        // rank.  Barrier B: all of that has landed, nobody reads voxels any more -> the next frame may integrate; the ICP maps of this
+        // rank's slab follow (every rank receives every row while tracking is on, then barrier C).
         shard_barrier(e);
         tsdf::raycast_sharded(e->scene, e->view, e->cam, W, H, e->minmaxLive, true, st);
         shard_barrier(e);
@@ -499,6 +540,7 @@ extern "C" int gsb_tsdf_process_frame(gsb_tsdf_t *e, const uint8_t *rgba_host, c
     if (!e || !rgba_host || !depth_mm_host)
         return gs_set_error(__FILE__, __LINE__, "null argument");
     const size_t P = (size_t)e->cfg.width * e->cfg.height;
+    E_CUDA(cudaSetDevice(e->cfg.device));
     // B1: ITMViewBuilder::UpdateView H2D (ITMViewBuilder_CUDA.cu:60-61); async when the host buffers are pinned
     E_CUDA(cudaMemcpyAsync(e->rgba, rgba_host, P * 4, cudaMemcpyHostToDevice, e->stream));
     E_CUDA(cudaMemcpyAsync(e->depth_mm, depth_mm_host, P * 2, cudaMemcpyHostToDevice, e->stream));
@@ -531,6 +573,7 @@ extern "C" int gsb_tsdf_run_raycast(gsb_tsdf_t *e, const float *c2w, float fx, f
     cam.invM = p.get_invM();
     cam.fx = fx, cam.fy = fy, cam.cx = cx, cam.cy = cy;
     const int W = e->cfg.width, H = e->cfg.height;
+    E_CUDA(cudaSetDevice(e->cfg.device));
     if (e->world == 1)
     {
         tsdf::expected_depth_free(e->scene, cam, W, H, e->minmaxFree, e->stream);
@@ -665,6 +708,7 @@ extern "C" int gsb_tsdf_run_stage(gsb_tsdf_t *e, int stage)
 {
     if (!e->haveFrame)
         return gs_set_error(__FILE__, __LINE__, "run_stage needs a processed frame");
+    E_CUDA(cudaSetDevice(e->cfg.device));
     const int W = e->cfg.width, H = e->cfg.height;
     switch (stage)
     {

@@ -17,6 +17,7 @@
 //  * the depth short->float conversion (B1) is fused into the allocation pass;
 //  * voxel blocks are streamed through shared memory with TMA bulk copies in the integrate kernel.
 #include <stdlib.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tsdf.h"
@@ -548,7 +549,7 @@ constexpr int INT_DESC = 128; // descriptor ring (two halves of 64)
 __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict__ vba, const HashEntry *__restrict__ table,
                                                                 const int *__restrict__ visIds, const int *__restrict__ nVis,
                                                                 IntegrateParams P, const float *__restrict__ depth,
-                                                                const uchar4 *__restrict__ rgb)
+                                                                const uchar4 *__restrict__ rgb, const __grid_constant__ PeerVbas push)
 {
     __shared__ __align__(128) uint2 buf[INT_STAGES][SDF_BLOCK_SIZE3];
     __shared__ __align__(8) unsigned long long full[INT_STAGES];
@@ -651,6 +652,9 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
         if (tid == 0 && ptr >= 0 && sDirty[s])
         {
             tma_store_1d(vba + (size_t)ptr * SDF_BLOCK_SIZE3, &buf[s][0], SDF_BLOCK_SIZE3 * 8);
+            // sharded scene, mode 1: the updated block also goes into every other rank's array (one 4 KB bulk store each, over NVLink)
+            for (int q = 0; q < push.n; q++)
+                tma_store_1d(push.p[q] + (size_t)ptr * SDF_BLOCK_SIZE3, &buf[s][0], SDF_BLOCK_SIZE3 * 8);
             tma_store_commit();
         }
     }
@@ -1231,52 +1235,89 @@ __global__ void __launch_bounds__(256) k_raycast(float4 *__restrict__ pointsRay,
     }
 }
 
-// Sharded raycast (world > 1): this rank marches the rays of its slab of rows [row0, row0 + 8 * gridDim.y); voxels are read from the rank that
-// owns their block (peer loads over NVLink -- the hash table is local).  LIVE: visibility marks go to every rank, the result stays local
-// except the two rows next to a slab border, which the neighbour's ICP-map kernel needs for its finite differences.  Free view: every
-// rank receives every row (the all-gather is the kernel's own output store), colour included.
-template <bool LIVE>
+// Sharded raycast (world > 1): the image is dealt to the ranks in strips of 8 rows, strip t to rank t mod world (interleaved so that near and
+// far parts of the view, which cost very different numbers of march steps, are spread evenly); this rank marches the rays of its strips.
+// Voxels are read from the rank that owns their block (mode 0: peer loads over NVLink, the hash table is local) or from the local copy
+// (mode 1).  Every rank receives every row: the all-gather is the kernel's own output store (128-byte runs per warp).  LIVE: visibility
+// marks go to every rank as well.
+template <bool LIVE, bool REPL>
 __global__ void __launch_bounds__(256) k_raycast_sharded(const __grid_constant__ ShardView v, const HashEntry *__restrict__ table, int W, int H,
-                                                          int row0, int row1, Mat4 invM, float4 invProj, float oneOverVoxelSize, float mu,
+                                                          Mat4 invM, float4 invProj, float oneOverVoxelSize, float mu,
                                                           const float2 *__restrict__ minmax, int mmW)
 {
+    // the CTA's 32 x 8 pixel tile is staged in shared memory and leaves as bulk copies (one 512-byte run per tile row and destination rank):
+    // per-thread 16-byte stores into peer memory reach a small fraction of the NVLink rate, TMA bulk stores do not have that problem
+    __shared__ __align__(128) float4 sOut[8][32];
+    __shared__ __align__(128) uchar4 sCol[8][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int x = blockIdx.x * 32 + (wid & 3) * 8 + (lane & 7);
-    int y = row0 + blockIdx.y * 8 + (wid >> 2) * 4 + (lane >> 3);
-    if (x >= W || y >= row1)
-        return;
-    float2 mm = __ldg(&minmax[(x >> 3) + (y >> 3) * mmW]);
-    const VbaSharded vba = {&v};
-    float3 pt;
-    float conf;
-    RayCounters cnt;
-    bool found;
-    if (LIVE)
+    const int tx = (wid & 3) * 8 + (lane & 7), ty = (wid >> 2) * 4 + (lane >> 3);
+    const int x0 = blockIdx.x * 32, y0 = (blockIdx.y * v.world + v.rank) * 8;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool inside = x < W && y < H;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 col = make_uchar4(0, 0, 0, 0);
+    if (inside)
     {
-        const MarkAll mark = {&v};
-        found = cast_ray<true, false>(vba, table, mark, x, y, invM, invProj, oneOverVoxelSize, mu, mm, pt, conf, cnt);
-    }
-    else
-    {
-        const MarkNone mark;
-        found = cast_ray<false, false>(vba, table, mark, x, y, invM, invProj, oneOverVoxelSize, mu, mm, pt, conf, cnt);
-    }
-    const int loc = x + y * W;
-    const float4 out = make_float4(pt.x, pt.y, pt.z, found ? conf + 1.0f : 0.0f);
-    if (LIVE)
-    {
-        v.rayLive[v.rank][loc] = out;
-        if (v.rank > 0 && y < row0 + 2)
-            v.rayLive[v.rank - 1][loc] = out;
-        if (v.rank < v.world - 1 && y >= row1 - 2)
-            v.rayLive[v.rank + 1][loc] = out;
-    }
-    else
-    {
-        uchar4 col = make_uchar4(0, 0, 0, 0);
-        if (found && (conf + 1.0f) > 0)
+        float2 mm = __ldg(&minmax[(x >> 3) + (y >> 3) * mmW]);
+        // mode 1: every rank holds every block (the integrate kernel stored them), only the rows are split
+        typename std::conditional<REPL, VbaLocal, VbaSharded>::type vba;
+        if constexpr (REPL)
+            vba.vba = v.vba[v.rank];
+        else
+            vba.v = &v;
+        float3 pt;
+        float conf;
+        RayCounters cnt;
+        bool found;
+        if (LIVE)
+        {
+            const MarkAll mark = {&v};
+            found = cast_ray<true, false>(vba, table, mark, x, y, invM, invProj, oneOverVoxelSize, mu, mm, pt, conf, cnt);
+        }
+        else
+        {
+            const MarkNone mark;
+            found = cast_ray<false, false>(vba, table, mark, x, y, invM, invProj, oneOverVoxelSize, mu, mm, pt, conf, cnt);
+        }
+        out = make_float4(pt.x, pt.y, pt.z, found ? conf + 1.0f : 0.0f);
+        if (!LIVE && found && (conf + 1.0f) > 0)
             col = colour_interp(vba, table, pt);
-        for (int q = 0; q < v.world; q++)
+    }
+    const bool bulk = (W & 3) == 0 && v.probe != 2;   // 16-byte alignment of every tile row of the colour image
+    if (bulk)
+    {
+        sOut[ty][tx] = out;
+        if (!LIVE)
+            sCol[ty][tx] = col;
+        fence_proxy_async();
+        __syncthreads();
+        // thread r < 8 sends tile row r to every rank (its own included)
+        if (threadIdx.x < 8 && y0 + (int)threadIdx.x < H)
+        {
+            const int r = threadIdx.x;
+            const int npx = min(32, W - x0);
+            const size_t loc = (size_t)x0 + (size_t)(y0 + r) * W;
+            for (int q = 0; q < v.world; q++)
+            {
+                if (v.probe == 1 && q != v.rank)
+                    continue;
+                tma_store_1d((LIVE ? v.rayLive[q] : v.rayFree[q]) + loc, &sOut[r][0], (unsigned)npx * 16u);
+                if (!LIVE)
+                    tma_store_1d(v.imageFree[q] + loc, &sCol[r][0], (unsigned)npx * 4u);
+            }
+            tma_store_commit();
+            tma_store_wait_all();
+        }
+        return;
+    }
+    if (!inside)
+        return;
+    const int loc = x + y * W;
+    for (int q = 0; q < v.world; q++)
+    {
+        if (LIVE)
+            v.rayLive[q][loc] = out;
+        else
         {
             v.rayFree[q][loc] = out;
             v.imageFree[q][loc] = col;
@@ -1392,25 +1433,39 @@ template <bool PUSH_ALL>
 __global__ void __launch_bounds__(256) k_icp_maps_sharded(const __grid_constant__ ShardView v, int W, int H, int row0, int row1, float voxelSize,
                                                            float3 light)
 {
-    int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    int y = row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= row1)
-        return;
-    float4 pm, nm;
-    icp_map_pixel(v.rayLive[v.rank], x, y, W, H, voxelSize, light, pm, nm);
-    const int loc = x + y * W;
-    if (PUSH_ALL)
+    __shared__ __align__(128) float4 sP[8][32], sN[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 32, y0 = row0 + blockIdx.y * 8;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool inside = x < W && y < row1;
+    float4 pm = make_float4(0, 0, 0, -1.0f), nm = pm;
+    if (inside)
+        icp_map_pixel(v.rayLive[v.rank], x, y, W, H, voxelSize, light, pm, nm);
+    if (!PUSH_ALL)
     {
+        if (inside)
+        {
+            v.pointsMap[v.rank][x + y * W] = pm;
+            v.normalsMap[v.rank][x + y * W] = nm;
+        }
+        return;
+    }
+    // every rank receives every row: the tile leaves as bulk copies, one 512-byte run per tile row, map and destination rank
+    sP[ty][tx] = pm, sN[ty][tx] = nm;
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x < 8 && y0 + (int)threadIdx.x < row1)
+    {
+        const int r = threadIdx.x;
+        const unsigned bytes = (unsigned)min(32, W - x0) * 16u;
+        const size_t loc = (size_t)x0 + (size_t)(y0 + r) * W;
         for (int q = 0; q < v.world; q++)
         {
-            v.pointsMap[q][loc] = pm;
-            v.normalsMap[q][loc] = nm;
+            tma_store_1d(v.pointsMap[q] + loc, &sP[r][0], bytes);
+            tma_store_1d(v.normalsMap[q] + loc, &sN[r][0], bytes);
         }
-    }
-    else
-    {
-        v.pointsMap[v.rank][loc] = pm;
-        v.normalsMap[v.rank][loc] = nm;
+        tma_store_commit();
+        tma_store_wait_all();
     }
 }
 
@@ -1482,12 +1537,16 @@ void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, c
     // sharded scene: only the visible blocks this rank owns (per-block independent work, no exchange)
     const int *ids = s.world > 1 ? s.visIdsOwn : s.visIds;
     const int *nIds = s.world > 1 ? s.state + 6 : s.state + 2;
-    if (variant == 1)
+    PeerVbas push;
+    push.n = s.nPush;
+    for (int q = 0; q < s.nPush; q++)
+        push.p[q] = s.pushVba[q];
+    if (variant == 1 && push.n == 0)
         k_integrate_direct<<<148 * 4, 512, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
-    else if (variant == 2)
+    else if (variant == 2 && push.n == 0)
         k_integrate_ws<<<148 * 4, WS_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
     else
-        k_integrate_tma<<<148 * 5, INT_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
+        k_integrate_tma<<<148 * 5, INT_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba, push);
 }
 
 void expected_depth_live(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st)
@@ -1530,19 +1589,23 @@ void raycast(const Scene &s, const Camera &cam, int W, int H, const float2 *minm
 
 void raycast_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, const float2 *minmax, bool live, cudaStream_t st)
 {
-    int y0, y1;
-    slab_rows(H, v.rank, v.world, y0, y1);
-    if (y1 <= y0)
+    const int strips = cdiv(H, 8);
+    const int mine = strips > v.rank ? (strips - v.rank + v.world - 1) / v.world : 0;   // strips t = rank, rank + world, ...
+    if (mine <= 0)
         return;
-    dim3 grid(cdiv(W, 32), cdiv(y1 - y0, 8));
+    dim3 grid(cdiv(W, 32), mine);
     float4 invProj = make_float4(1.0f / cam.fx, 1.0f / cam.fy, -cam.cx, -cam.cy);
     float oneOverVoxel = 1.0f / s.voxelSize;
     int mmW = cdiv(W, 8);
     GS_COUNT_LAUNCHES(1);
-    if (live)
-        k_raycast_sharded<true><<<grid, 256, 0, st>>>(v, s.table, W, H, y0, y1, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
+    if (live && v.replicated)
+        k_raycast_sharded<true, true><<<grid, 256, 0, st>>>(v, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
+    else if (live)
+        k_raycast_sharded<true, false><<<grid, 256, 0, st>>>(v, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
+    else if (v.replicated)
+        k_raycast_sharded<false, true><<<grid, 256, 0, st>>>(v, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
     else
-        k_raycast_sharded<false><<<grid, 256, 0, st>>>(v, s.table, W, H, y0, y1, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
+        k_raycast_sharded<false, false><<<grid, 256, 0, st>>>(v, s.table, W, H, cam.invM, invProj, oneOverVoxel, s.mu, minmax, mmW);
 }
 
 void icp_maps_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, bool pushAll, cudaStream_t st)

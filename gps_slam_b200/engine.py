@@ -77,6 +77,8 @@ def load_library():
     L.gsb_tsdf_shard_attach.argtypes = [C.c_void_p, C.c_void_p]
     L.gsb_tsdf_shard_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.gsb_tsdf_shard_error.argtypes = [C.c_void_p]
+    L.gsb_tsdf_shard_set_mode.argtypes = [C.c_void_p, C.c_int]
+    L.gsb_tsdf_shard_probe.argtypes = [C.c_void_p, C.c_int]
     L.gsb_tsdf_shard_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     L.gsb_tsdf_reset.argtypes = [C.c_void_p]
     L.gsb_tsdf_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -216,11 +218,15 @@ class TsdfEngine:
         arr = (C.c_void_p * self.world)(*[e.h_ for e in engines])
         _check(self.L.gsb_tsdf_shard_attach_local(self.h_, arr))
 
+    def set_shard_mode(self, mode):
+        """0: storage-sharded (peer reads in the raycast); 1: owner integrates and stores the block into every rank (local reads)"""
+        _check(self.L.gsb_tsdf_shard_set_mode(self.h_, mode))
+
     def shard_error(self):
         return int(self.L.gsb_tsdf_shard_error(self.h_))
 
     def shard_rows(self):
-        """image rows [row0, row1) this rank raycasts"""
+        """rows [row0, row1) of the ICP maps this rank computes"""
         r0, r1 = C.c_int(), C.c_int()
         _check(self.L.gsb_tsdf_shard_info(self.h_, None, None, C.byref(r0), C.byref(r1)))
         return r0.value, r1.value

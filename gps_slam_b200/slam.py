@@ -80,7 +80,7 @@ class BufferPool:
 
 class SlamPipeline:
     def __init__(self, intr, mode="train", device=0, stream=None, rank=0, world=1, cfg=None, seed=42, gs_capacity=1 << 21, use_gt_pose=True,
-                 tracker=1, overlap=True, exchange=None, comm=None):
+                 tracker=1, overlap=True, exchange=None, comm=None, tsdf_shard=None):
         """use_gt_pose=False: online tracking (TSDF.use_gt_pose: false) with the extended (1) or icp (2) tracker.
         world > 1: Gaussians sharded across ranks (parallel.py); torch.distributed must be initialised by the caller."""
         self.intr, self.mode, self.rank, self.world = intr, mode, rank, world
@@ -88,8 +88,15 @@ class SlamPipeline:
         c = self.cfg
         self.device = torch.device("cuda", device)
         self.use_gt_pose = use_gt_pose
-        self.tsdf = E.TsdfEngine(intr, voxel_size=c["voxel_size"], mu=c["trunc_dist"], view_frustum_min=c["viewFrustum_min"],
-                                 view_frustum_max=c["viewFrustum_max"], tracker=0 if use_gt_pose else tracker, device=device)
+        # world > 1: the voxel hash is sharded by spatial block as well (csrc/tsdf.h: replicated hash table, owned-block integrate, row-slab
+        # raycasts over peer memory); GSB_TSDF_SHARD=0 keeps a full replica of the map on every rank (A/B timing)
+        self.tsdf_sharded = world > 1 and (tsdf_shard if tsdf_shard is not None else os.environ.get("GSB_TSDF_SHARD", "1") != "0")
+        tkw = dict(voxel_size=c["voxel_size"], mu=c["trunc_dist"], view_frustum_min=c["viewFrustum_min"], view_frustum_max=c["viewFrustum_max"],
+                   tracker=0 if use_gt_pose else tracker)
+        if self.tsdf_sharded:
+            self.tsdf = parallel.make_sharded_tsdf(intr, rank, world, device, **tkw)
+        else:
+            self.tsdf = E.TsdfEngine(intr, device=device, **tkw)
         self.W, self.H = intr["width"], intr["height"]
         # multi-GPU exchange of the partial images: "peer" (stores into peer memory below the C ABI, csrc/gs_comm.h) or "nccl" (all-reduce
         # between two C-ABI calls).  comm: an already attached PeerComm (tests with several engines in one process)
@@ -418,12 +425,15 @@ class SlamPipeline:
     def parallelism(self):
         if self.world == 1:
             return "single GPU"
+        tsdf = ("voxel hash sharded by spatial block (owner = hashIndex(blockPos) mod %d): hash table / allocation replicated, each rank integrates "
+                "the blocks it owns, raycasts split by image rows with peer-memory voxel reads and row stores into every rank, 2 flag barriers "
+                "per frame" % self.world) if self.tsdf_sharded else "TSDF replicated"
         if self.exchange == "peer":
             return ("Gaussians sharded by spatial block over %d GPUs; per optimiser iteration the rasteriser stores tile partial sums into the owner "
                     "rank's memory over NVLink (reduce-scatter), the owner composites and stores dL/d(render) into every rank (all-gather), 2 flag "
-                    "barriers through peer memory, no NCCL call; TSDF replicated" % self.world)
-        return ("Gaussians sharded by spatial block over %d GPUs, one NCCL all-reduce of the [H,W,5] partial image per optimiser iteration; "
-                "TSDF replicated" % self.world)
+                    "barriers through peer memory, no NCCL call; %s" % (self.world, tsdf))
+        return ("Gaussians sharded by spatial block over %d GPUs, one NCCL all-reduce of the [H,W,5] partial image per optimiser iteration; %s"
+                % (self.world, tsdf))
 
     def tracking_stats(self, poses, total):
         """online-tracking summary (BASELINE.json config 3): translation error of the tracked poses against the generator's, LM
@@ -494,6 +504,12 @@ class SlamPipeline:
         for name, st in (("tsdf_allocate(6 kernels)", 0), ("tsdf_integrate", 1), ("tsdf_expected_depth(2)", 2), ("tsdf_raycast", 3),
                          ("tsdf_icp_maps", 4)):
             table[name] = self._time(stream, lambda st=st: self.tsdf.run_stage(st), reps, flush) * 1e6
+        cams = [c for c in self.opt_cams if c.depth_map is not None]
+        if cams:
+            # free-view raycast as runRaycastByCam issues it (expected depths over the whole table + raycast + colour; sharded: plus its two
+            # barriers and the row stores into every rank)
+            c2w_free = syn.c2w_to_colmajor(cams[-1].c2w_slam)
+            table["tsdf_free_view_raycast"] = self._time(stream, lambda: self.tsdf.runRaycast(c2w_free, self.intr), reps, flush) * 1e6
         fresh = self._fresh_frame_stages(stream, fresh_frames) if fresh_frames is not None else None
         if fresh:
             # the in-loop figure: fresh frames, events inside ProcessFrame (no L2 flush needed: every frame is new data and V x 8 KB
@@ -529,6 +545,18 @@ class SlamPipeline:
             g.run_stage(4)
         table["gs_train_step(7 kernels, no flush)"] = self._time(
             stream, lambda: g.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image), reps, flush) * 1e6
+        if self.comm is not None and self.world > 1:
+            table["gs_exchange_barrier"] = self._time(stream, lambda: self.comm.barrier(stream.cuda_stream), reps, flush) * 1e6
+        # where a 10-frame step goes, from the per-stage device times above (stages of the two streams overlap in the real loop, so the
+        # parts add up to more than ms_per_step when the overlap works and to about ms_per_step when the SMs are the limit)
+        c = self.cfg
+        per_frame = sum(v for k, v in (fresh or {}).items() if k in ("track", "allocate(6 kernels)", "integrate", "expected_depth(2)", "raycast", "icp_maps"))
+        n_free = len(self.opt_cams)
+        self.breakdown = {"tsdf_fuse_ms": c["local_opt_interval"] * per_frame * 1e-3,
+                          "tsdf_free_view_raycasts_ms": n_free * table.get("tsdf_free_view_raycast", 0.0) * 1e-3,
+                          "gaussian_iterations_ms": c["local_opt_iters"] * table["gs_train_step(7 kernels, no flush)"] * 1e-3,
+                          "of_which_exchange_barriers_ms": 2 * c["local_opt_iters"] * table.get("gs_exchange_barrier", 0.0) * 1e-3,
+                          "free_view_raycasts_per_step": n_free, "frames_per_step": c["local_opt_interval"], "iterations_per_step": c["local_opt_iters"]}
         cnt = g.counters()
         I, n_vis = int(cnt[0]), int(cnt[4])
         t = table["gs_raster_bwd"] * 1e-6
@@ -537,4 +565,4 @@ class SlamPipeline:
         return {"kernel": "k_raster_bwd", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                 "traffic": None, "algorithmic_bytes": alg, "avg_launch_us": t * 1e6,
                 "units": {"pixels": P, "isects": I, "visible_gaussians": n_vis, "gaussians": self.n_gauss},
-                "kernels_us": table, "tsdf_integrate": integrate}
+                "kernels_us": table, "step_breakdown": self.breakdown, "tsdf_integrate": integrate}

@@ -64,16 +64,22 @@ int gsb_tsdf_create(const gsb_tsdf_config_t *cfg, gsb_tsdf_t **out);
  * raycasts are split by image rows, read the voxels from their owner over NVLink peer memory (castRay, ITMVisualisationEngine_Shared.h:
  * 122-221) and store their rows straight into the other ranks' images; cross-GPU ordering is two flag barriers per frame through peer
  * memory.  Every rank must issue the same sequence of process_frame / run_raycast calls.  Results are bit-identical to world == 1:
- * hash table, visible list, poses, free-view vertex / colour images on EVERY rank; GSB_TSDF_VOXELS holds the blocks this rank owns;
- * live raycast and ICP maps hold this rank's rows (gsb_tsdf_shard_info) unless tracking is on (then every rank holds all rows of the maps).
+ * hash table, visible list, poses, live and free-view vertex / colour images on EVERY rank; GSB_TSDF_VOXELS holds the blocks this rank owns
+ * (mode 1: all blocks); the ICP maps hold this rank's rows (gsb_tsdf_shard_info) unless tracking is on (then every rank holds all rows).
  * After create_sharded the peers' segments must be mapped once: between processes exchange the 64-byte handles of shard_export (any
  * transport) and call shard_attach(handles of all ranks in rank order); engines inside one process use shard_attach_local. */
 int gsb_tsdf_create_sharded(const gsb_tsdf_config_t *cfg, int rank, int world, gsb_tsdf_t **out);
 int gsb_tsdf_shard_export(gsb_tsdf_t *e, void *handle64);
 int gsb_tsdf_shard_attach(gsb_tsdf_t *e, const void *handles /* world x 64 bytes */);
 int gsb_tsdf_shard_attach_local(gsb_tsdf_t *e, gsb_tsdf_t *const *peers /* world engines in rank order */);
+/* mode 0: storage-sharded -- a block's voxels exist on its owner only, raycasts read them over NVLink (1/world of the voxel memory
+ * per GPU).  mode 1 (default): owner computes, everybody stores -- the integrate kernel writes each block it updated into every rank's array (4 KB TMA
+ * bulk stores over NVLink), every rank keeps a complete copy, raycasts (still split by rows) read local memory.  Same results either way;
+ * every rank must use the same mode; only on an empty scene. */
+int gsb_tsdf_shard_set_mode(gsb_tsdf_t *e, int mode);
+int gsb_tsdf_shard_probe(gsb_tsdf_t *e, int what);   /* measurement aid: 0 normal, 1 raycast rows stay local, 2 per-thread peer stores */
 int gsb_tsdf_shard_error(gsb_tsdf_t *e);   /* non-zero: a cross-GPU barrier or exchange timed out (a peer never arrived) */
-int gsb_tsdf_shard_info(gsb_tsdf_t *e, int *rank, int *world, int *row0, int *row1);   /* image rows [row0, row1) this rank raycasts */
+int gsb_tsdf_shard_info(gsb_tsdf_t *e, int *rank, int *world, int *row0, int *row1);   /* rows [row0, row1) of the ICP maps this rank computes */
 void gsb_tsdf_destroy(gsb_tsdf_t *e);
 int gsb_tsdf_reset(gsb_tsdf_t *e);                               /* ITMBasicEngine::resetAll */
 int gsb_tsdf_set_stream(gsb_tsdf_t *e, void *cuda_stream);       /* cudaStream_t; NULL = private stream */
