@@ -55,21 +55,13 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     // The 15x3 higher-order SH coefficients of the warp's 32 consecutive Gaussians are one contiguous 5,760-byte run: one TMA bulk
-    // copy per warp brings it into shared memory while the projection math below runs; lanes then read their own row at stride 45
-    // (odd -> conflict free).  Buffers are padded to a multiple of 128 Gaussians (and the grid never exceeds that), so the full run
-    // and every parameter below are readable for any g of the grid: all loads are requested before anything depends on them, the
-    // Gaussian count included.
+    // copy per warp brings it into shared memory; lanes then read their own row at stride 45 (odd -> conflict free).  Buffers are
+    // padded to a multiple of 128 Gaussians (and the grid never exceeds that), so the full run and every parameter below are readable
+    // for any g of the grid: the small parameters are requested before anything depends on them, the Gaussian count included.
     __shared__ __align__(128) float sRest[4][32 * 45];
     __shared__ unsigned long long sBar[4];
     float *rest = sRest[threadIdx.x >> 5];
     unsigned long long *bar = &sBar[threadIdx.x >> 5];
-    const bool warpLive = true;
-    if (lane == 0)
-    {
-        tma::mbar_init(bar, 1);
-        tma::mbar_expect_tx(bar, 32 * 45 * 4);
-        tma::load_1d(rest, p.rest + (size_t)(g - lane) * 45, 32 * 45 * 4, bar);
-    }
     float mean[3];
     mean[0] = p.means[g * 3 + 0], mean[1] = p.means[g * 3 + 1], mean[2] = p.means[g * 3 + 2];
     const float ls0 = p.scales[g * 3 + 0], ls1 = p.scales[g * 3 + 1], ls2 = p.scales[g * 3 + 2];
@@ -78,7 +70,6 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
     const float dc0 = p.dc[g * 3 + 0], dc1 = p.dc[g * 3 + 1], dc2 = p.dc[g * 3 + 2];
     const int nGauss = *nDev;
     const bool inRange = g < nGauss;
-    __syncwarp();
     Proj o;
     o.radius = 0;
     if (inRange)
@@ -90,8 +81,20 @@ __global__ void __launch_bounds__(128) k_project_sh(ParamPtrs p, const int *__re
     const bool vis = o.radius > 0;
     const unsigned full = 0xffffffffu;
     const unsigned vm = __ballot_sync(full, vis);
-    if (warpLive)
-        tma::mbar_wait(bar, 0); // always, also when nothing is visible: the CTA must not retire with a copy in flight
+    // The SH run is 76 % of the bytes this kernel could read, and in a grown map most warps see nothing (Gaussians are appended in raster
+    // order: neighbours in id are neighbours in space): it is fetched only by warps with a visible Gaussian, after the projection
+    // (the other resident warps cover the copy's latency; an earlier, cheaper test cannot be exact -- the cull uses the unclamped radius)
+    if (vm)
+    {
+        if (lane == 0)
+        {
+            tma::mbar_init(bar, 1);
+            tma::mbar_expect_tx(bar, 32 * 45 * 4);
+            tma::load_1d(rest, p.rest + (size_t)(g - lane) * 45, 32 * 45 * 4, bar);
+        }
+        __syncwarp();
+        tma::mbar_wait(bar, 0); // every lane: the CTA must not retire with the copy in flight
+    }
     int nItems = 0, rectXY = 0, rectWH = 0;
     int bits = 0;
     float col[3] = {0.f, 0.f, 0.f};
@@ -464,15 +467,11 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     const int g = g0 + lane;
     if (blockIdx.x == 0 && threadIdx.x == 0)
         counters[CNT_ITEMS] = 0; // re-arm for the next projection
-    // Everything whose address does not depend on data is requested up front (g < capacity: the grid covers nUpper <= capacity and
-    // buffers are padded to 128 Gaussians), so the kernel pays one memory round trip instead of four chained ones:
-    // record + raster gradients + state flag now, optimiser moments pulled into L2 for the Adam step at the end.
-    const float4 q0r = __ldg(&recs[g].q0), q1r = __ldg(&recs[g].q1), q2r = __ldg(&recs[g].q2);
-    const float4 sg0 = __ldg(&grads[g].g0), sg1 = __ldg(&grads[g].g1), sg2 = __ldg(&grads[g].g2);
+    // In a grown map four Gaussians out of five are neither visible nor carry optimiser state: only the 16-byte head of the record (the
+    // radius) and the state flag are read for everybody; the rest of the record, the raster gradients and the moments follow for the
+    // lanes that need them (one more round trip for those, 180 bytes less for all the others).
+    const float4 q0r = __ldg(&recs[g].q0);
     const unsigned char tch = touched[g];
-    prefetch_l2(m.means + g * 3), prefetch_l2(v.means + g * 3), prefetch_l2(m.scales + g * 3), prefetch_l2(v.scales + g * 3);
-    prefetch_l2(m.dc + g * 3), prefetch_l2(v.dc + g * 3), prefetch_l2(m.quats + g * 4), prefetch_l2(v.quats + g * 4);
-    prefetch_l2(m.opac + g), prefetch_l2(v.opac + g);
     const int N = *nDev;
     if (g0 >= N)
         return;
@@ -481,6 +480,18 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
     const int radius = __float_as_int(q0.w);
     const bool vis = inRange && radius > 0;
     const bool had = inRange && tch != 0;
+    float4 q1r = make_float4(0.f, 0.f, 0.f, 0.f), q2r = q1r, sg0 = q1r, sg1 = q1r, sg2 = q1r;
+    if (vis)
+    {
+        q1r = __ldg(&recs[g].q1), q2r = __ldg(&recs[g].q2);
+        sg0 = __ldg(&grads[g].g0), sg1 = __ldg(&grads[g].g1), sg2 = __ldg(&grads[g].g2);
+    }
+    if (had)
+    {
+        prefetch_l2(m.means + g * 3), prefetch_l2(v.means + g * 3), prefetch_l2(m.scales + g * 3), prefetch_l2(v.scales + g * 3);
+        prefetch_l2(m.dc + g * 3), prefetch_l2(v.dc + g * 3), prefetch_l2(m.quats + g * 4), prefetch_l2(v.quats + g * 4);
+        prefetch_l2(m.opac + g), prefetch_l2(v.opac + g);
+    }
     const unsigned full = 0xffffffffu;
     const unsigned visMask = __ballot_sync(full, vis);
     // SH coefficient run of the warp's 32 Gaussians by one TMA bulk copy, overlapped with the projection re-computation below -- only
@@ -542,18 +553,14 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
         float o = q0.z;
         gop = sg.g0.z * o * (1.0f - o);
     }
-    if (inRange)
+    if (vis)
     {
-        const int flag = (vis ? 1 : 0) | (had ? 2 : 0);
         float4 *a = aux + (size_t)g * (AUX_FLOATS / 4);
-        if (vis)
-        {
-            a[0] = make_float4(basis[1], basis[2], basis[3], basis[4]);
-            a[1] = make_float4(basis[5], basis[6], basis[7], basis[8]);
-            a[2] = make_float4(basis[9], basis[10], basis[11], basis[12]);
-            a[3] = make_float4(basis[13], basis[14], basis[15], vcol[0]);
-        }
-        a[4] = make_float4(vcol[1], vcol[2], __int_as_float(flag), 0.f);
+        a[0] = make_float4(basis[1], basis[2], basis[3], basis[4]);
+        a[1] = make_float4(basis[5], basis[6], basis[7], basis[8]);
+        a[2] = make_float4(basis[9], basis[10], basis[11], basis[12]);
+        a[3] = make_float4(basis[13], basis[14], basis[15], vcol[0]);
+        a[4] = make_float4(vcol[1], vcol[2], 0.f, 0.f);
     }
     if (haveDbg && inRange)
     {
@@ -619,11 +626,14 @@ __global__ void __launch_bounds__(ADAM_WARPS * 32, 4) k_bwd_params(ParamPtrs p, 
         reinterpret_cast<float4 *>(m.quats)[g] = make_float4(M13[9], M13[10], M13[11], M13[12]);
         reinterpret_cast<float4 *>(v.quats)[g] = make_float4(V13[9], V13[10], V13[11], V13[12]);
         p.opac[g] = po, m.opac[g] = mo, v.opac[g] = vo;
-        touched[g] = 1;
+        // state byte: bit 0 = has optimiser state (from now on), bit 1 = the state was created by this step (moments start from zero),
+        // bit 2 = received a gradient in this step.  k_adam_rest takes its per-Gaussian decisions from this one byte.
+        touched[g] = (unsigned char)(1 | (had ? 0 : 2) | (vis ? 4 : 0));
     }
 }
 
-__device__ __forceinline__ void adam_rest4(float4 &P, float4 &M, float4 &V, int i4, int N, const float *__restrict__ aux, const AdamStep &step)
+__device__ __forceinline__ void adam_rest4(float4 &P, float4 &M, float4 &V, int i4, int N, const float *__restrict__ aux,
+                                           const unsigned char *__restrict__ state, const AdamStep &step)
 {
     float pv[4] = {P.x, P.y, P.z, P.w}, mv[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
 #pragma unroll
@@ -634,12 +644,12 @@ __device__ __forceinline__ void adam_rest4(float4 &P, float4 &M, float4 &V, int 
         if (gl >= N)
             continue;
         const float *a = aux + (size_t)gl * AUX_FLOATS;
-        const int fl = __float_as_int(__ldg(a + 18));
+        const int fl = __ldg(state + gl);
         if (fl == 0)
             continue;
         const int k = e / 3, c = e - k * 3; // basis index k + 1
-        const float ge = (fl & 1) ? __ldg(a + k) * __ldg(a + 15 + c) : 0.f;
-        float mo = (fl & 2) ? mv[c4] : 0.f, vo = (fl & 2) ? vv[c4] : 0.f;
+        const float ge = (fl & 4) ? __ldg(a + k) * __ldg(a + 15 + c) : 0.f;
+        float mo = (fl & 2) ? 0.f : mv[c4], vo = (fl & 2) ? 0.f : vv[c4];
         pv[c4] = adam_update(pv[c4], ge, mo, vo, step.a, step.step_size[4]);
         mv[c4] = mo, vv[c4] = vo;
     }
@@ -649,7 +659,8 @@ __device__ __forceinline__ void adam_rest4(float4 &P, float4 &M, float4 &V, int 
 }
 
 __global__ void __launch_bounds__(256) k_adam_rest(float4 *__restrict__ pR, float4 *__restrict__ mR, float4 *__restrict__ vR,
-                                                    const float *__restrict__ aux, const int *__restrict__ nDev, AdamStep step)
+                                                    const float *__restrict__ aux, const unsigned char *__restrict__ state,
+                                                    const int *__restrict__ nDev, AdamStep step)
 {
     const int N = *nDev;
     const int total4 = (N * 45 + 3) / 4;
@@ -658,8 +669,8 @@ __global__ void __launch_bounds__(256) k_adam_rest(float4 *__restrict__ pR, floa
         return;
     // skip float4s whose (at most two) Gaussians are both inactive
     const int ga0 = (i4a * 4) / 45, ga1 = min((i4a * 4 + 3) / 45, N - 1), gb1 = min((i4b * 4 + 3) / 45, N - 1);
-    const int fa = __float_as_int(__ldg(aux + (size_t)ga0 * AUX_FLOATS + 18)) | __float_as_int(__ldg(aux + (size_t)ga1 * AUX_FLOATS + 18));
-    const int fb = (i4b < total4) ? (__float_as_int(__ldg(aux + (size_t)ga1 * AUX_FLOATS + 18)) | __float_as_int(__ldg(aux + (size_t)gb1 * AUX_FLOATS + 18))) : 0;
+    const int fa = __ldg(state + ga0) | __ldg(state + ga1);
+    const int fb = (i4b < total4) ? (__ldg(state + ga1) | __ldg(state + gb1)) : 0;
     float4 Pa, Ma, Va, Pb, Mb, Vb;
     if (fa)
         Pa = pR[i4a], Ma = mR[i4a], Va = vR[i4a];
@@ -667,12 +678,12 @@ __global__ void __launch_bounds__(256) k_adam_rest(float4 *__restrict__ pR, floa
         Pb = pR[i4b], Mb = mR[i4b], Vb = vR[i4b];
     if (fa)
     {
-        adam_rest4(Pa, Ma, Va, i4a, N, aux, step);
+        adam_rest4(Pa, Ma, Va, i4a, N, aux, state, step);
         pR[i4a] = Pa, mR[i4a] = Ma, vR[i4a] = Va;
     }
     if (fb)
     {
-        adam_rest4(Pb, Mb, Vb, i4b, N, aux, step);
+        adam_rest4(Pb, Mb, Vb, i4b, N, aux, state, step);
         pR[i4b] = Pb, mR[i4b] = Mb, vR[i4b] = Vb;
     }
 }
@@ -853,7 +864,7 @@ void bwd_params_adam(const ParamPtrs &p, const ParamPtrs &m, const ParamPtrs &v,
                                                                             counters);
     const long long total4 = ((long long)nUpper * 45 + 3) / 4;
     k_adam_rest<<<(int)((total4 + 511) / 512), 256, 0, st>>>(reinterpret_cast<float4 *>(p.rest), reinterpret_cast<float4 *>(m.rest),
-                                                              reinterpret_cast<float4 *>(v.rest), reinterpret_cast<const float *>(aux), nDev, step);
+                                                              reinterpret_cast<float4 *>(v.rest), reinterpret_cast<const float *>(aux), touched, nDev, step);
 }
 
 void reduce_loss(const float *lossTile, int T, double scale, double *out, cudaStream_t st)
