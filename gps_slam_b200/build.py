@@ -15,6 +15,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # (source, extra flags)
 SOURCES = [
     ("tsdf_kernels.cu", ["-fmad=false"]),
+    ("tsdf_mesh.cu", ["-fmad=false"]),
     ("tsdf_engine.cu", ["-fmad=false"]),
     ("icp_kernels.cu", ["-fmad=false"]),
     ("gs_project.cu", ["-fmad=false"]),

@@ -136,3 +136,20 @@ def load_scene(directory, tsdf):
     with open(os.path.join(scene, "last.txt")) as f:
         last_excess = int(f.read().split()[0])
     tsdf.load_scene(hash_entries, voxels, last_block, last_excess)
+
+
+def save_mesh_ply(path, tsdf):
+    """ITMBasicEngine::SaveSceneToMesh (reference InfiniTAM/ITMLib/Core/ITMBasicEngine.tpp:105-117): marching cubes on the device
+    (gsb_tsdf_mesh) + ITMMesh::WritePLY's ASCII layout (Objects/Meshing/ITMMesh.h:39-104): three vertices per triangle
+    "%f %f %f r g b" with colours truncated to uchar, then one "3 i j k" face per triangle.  Returns the triangle count."""
+    tri = tsdf.mesh().cpu().numpy()
+    n = len(tri)
+    pos = tri[:, :9].reshape(n * 3, 3)
+    col = (tri[:, 9:].reshape(n * 3, 3) * np.float32(255.0)).astype(np.int32).astype(np.uint8)   # static_cast<unsigned char>(c * 255)
+    with open(path, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\n" % (n * 3))
+        f.write("property float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n")
+        f.write("element face %d\nproperty list uchar int vertex_indices\nend_header\n" % n)
+        f.write("".join("%f %f %f %d %d %d\n" % (p[0], p[1], p[2], c[0], c[1], c[2]) for p, c in zip(pos, col)))
+        f.write("".join("3 %d %d %d\n" % (3 * i, 3 * i + 1, 3 * i + 2) for i in range(n)))
+    return n

@@ -96,5 +96,8 @@ void icp_maps(const Scene &s, const Camera &cam, int W, int H, const float4 *poi
 void raycast_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, const float2 *minmax, bool live, cudaStream_t st);
 void icp_maps_sharded(const Scene &s, const ShardView &v, const Camera &cam, int W, int H, bool pushAll, cudaStream_t st);
 void shard_barrier(const ShardView &v, unsigned epoch, int *errFlag, cudaStream_t st);
+// marching-cubes export (tsdf_mesh.cu)
+size_t mesh_scratch_bytes(const Scene &s);
+int mesh_scene(const Scene &s, const ShardView *view, void *scratch, float *outDev, long long maxTri, long long *nTriHost, cudaStream_t st);
 
 } // namespace tsdf

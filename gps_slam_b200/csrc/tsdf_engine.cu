@@ -679,6 +679,21 @@ extern "C" int gsb_tsdf_read(gsb_tsdf_t *e, int what, void *dst, size_t bytes)
     return 0;
 }
 
+// ITMBasicEngine::SaveSceneToMesh (Core/ITMBasicEngine.tpp:105-117) up to the file: marching cubes over every allocated block.
+// tri_dev: device buffer of max_tri triangles, 18 floats each (p0 p1 p2 in metres, c0 c1 c2 in 0..1), or NULL to count only.
+// The reference keeps at most max_tri - 1 triangles (noMaxTriangles rule of the CPU mesher); *n_tri = triangles written (or present).
+extern "C" int gsb_tsdf_mesh(gsb_tsdf_t *e, float *tri_dev, long long max_tri, long long *n_tri)
+{
+    if (!e || !n_tri || (tri_dev && max_tri <= 0))
+        return gs_set_error(__FILE__, __LINE__, "invalid argument");
+    E_CUDA(cudaSetDevice(e->cfg.device));
+    void *scratch = nullptr;
+    E_CUDA(cudaMalloc(&scratch, tsdf::mesh_scratch_bytes(e->scene)));
+    const int rc = tsdf::mesh_scene(e->scene, e->world > 1 ? &e->view : nullptr, scratch, tri_dev, max_tri, n_tri, e->stream);
+    cudaFree(scratch);
+    return rc;
+}
+
 // Measurement aid: CUDA events between the stages of ProcessFrame (track | allocate | integrate | expected depth | raycast | ICP maps)
 extern "C" int gsb_tsdf_enable_stage_timing(gsb_tsdf_t *e, int on)
 {

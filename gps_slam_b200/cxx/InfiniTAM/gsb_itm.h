@@ -12,7 +12,7 @@
 // (settings->deviceType is ignored) and construction fails loudly without a CUDA device.
 //
 // Not provided (SURVEY.md section 8 marks them out of scope): GetView / GetImage visualisations, swapping, surfel and multi-scene
-// engines, relocaliser, IMU / colour trackers; SaveSceneToMesh raises.
+// engines, relocaliser, IMU / colour trackers.
 #pragma once
 
 #include <cuda_runtime_api.h>
@@ -498,7 +498,45 @@ public:
     }
     gsb_tsdf_t *handle() { return h_; }                           // facade only
 
-    void SaveSceneToMesh(const char *) { DIEWITHEXCEPTION("gps_slam_b200: SaveSceneToMesh (marching cubes export) is not provided"); }
+    // Core/ITMBasicEngine.tpp:105-117 + ITMMesh::WritePLY (Objects/Meshing/ITMMesh.h:39-104): marching cubes on the device
+    // (gsb_tsdf_mesh: deterministic, the CPU mesher's triangle order, per-vertex colours like the CUDA mesher), then the reference's
+    // ASCII PLY: three vertices per triangle with uchar colours, one face per triangle
+    void SaveSceneToMesh(const char *fileName)
+    {
+        long long n = 0;
+        if (gsb_tsdf_mesh(h_, nullptr, 0, &n))
+            DIEWITHEXCEPTION(gsb_last_error());
+        float *dev = nullptr;
+        std::vector<float> tri((size_t)(n > 0 ? n : 1) * 18);
+        if (n > 0)
+        {
+            if (cudaMalloc((void **)&dev, (size_t)(n + 1) * 18 * sizeof(float)) != cudaSuccess)
+                DIEWITHEXCEPTION("gps_slam_b200: out of device memory for the mesh");
+            const int rc = gsb_tsdf_mesh(h_, dev, n + 1, &n);
+            if (!rc)
+                cudaMemcpy(tri.data(), dev, (size_t)n * 18 * sizeof(float), cudaMemcpyDeviceToHost);
+            cudaFree(dev);
+            if (rc)
+                DIEWITHEXCEPTION(gsb_last_error());
+        }
+        printf("write ply mesh...\n");
+        FILE *f = fopen(fileName, "w");
+        if (!f)
+            return;
+        fprintf(f, "ply\nformat ascii 1.0\nelement vertex %d\n", (int)(n * 3));
+        fprintf(f, "property float x\nproperty float y\nproperty float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n");
+        fprintf(f, "element face %d\nproperty list uchar int vertex_indices\nend_header\n", (int)n);
+        for (long long i = 0; i < n; i++)
+        {
+            const float *t = tri.data() + (size_t)i * 18;
+            for (int v = 0; v < 3; v++)
+                fprintf(f, "%f %f %f %d %d %d\n", t[v * 3], t[v * 3 + 1], t[v * 3 + 2], static_cast<unsigned char>(t[9 + v * 3] * 255),
+                        static_cast<unsigned char>(t[9 + v * 3 + 1] * 255), static_cast<unsigned char>(t[9 + v * 3 + 2] * 255));
+        }
+        for (long long i = 0; i < n; i++)
+            fprintf(f, "3 %d %d %d\n", (int)(i * 3), (int)(i * 3 + 1), (int)(i * 3 + 2));
+        fclose(f);
+    }
 
     // Core/ITMBasicEngine.tpp:119-171: the Scene/ directory in the reference's own file layout (see gps_slam_b200/checkpoint.py)
     void SaveToFile(const std::string &saveOutputDirectory)

@@ -79,6 +79,7 @@ def load_library():
     L.gsb_tsdf_shard_error.argtypes = [C.c_void_p]
     L.gsb_tsdf_shard_set_mode.argtypes = [C.c_void_p, C.c_int]
     L.gsb_tsdf_shard_probe.argtypes = [C.c_void_p, C.c_int]
+    L.gsb_tsdf_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]
     L.gsb_tsdf_shard_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     L.gsb_tsdf_reset.argtypes = [C.c_void_p]
     L.gsb_tsdf_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -202,6 +203,17 @@ class TsdfEngine:
         if getattr(self, "h_", None):
             self.L.gsb_tsdf_destroy(self.h_)
             self.h_ = None
+
+    def mesh(self, max_tri=None):
+        """SaveSceneToMesh up to the file: torch tensor [n, 18] on the engine's device (p0 p1 p2 in metres, c0 c1 c2 in 0..1), in the
+        reference CPU mesher's order"""
+        import torch
+        n = C.c_longlong()
+        _check(self.L.gsb_tsdf_mesh(self.h_, None, 0, C.byref(n)))
+        cap = (n.value + 1) if max_tri is None else max_tri
+        out = torch.empty((max(cap, 1), 18), dtype=torch.float32, device=torch.device("cuda", self.cfg.device))
+        _check(self.L.gsb_tsdf_mesh(self.h_, C.c_void_p(out.data_ptr()), cap, C.byref(n)))
+        return out[:n.value]
 
     # ---- sharded scene (SURVEY.md 8(e)) ----
     def export_handle(self):

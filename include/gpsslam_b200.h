@@ -138,6 +138,13 @@ int gsb_tsdf_read(gsb_tsdf_t *e, int what, void *dst_host, size_t bytes);
  * synchronises */
 int gsb_tsdf_counter(gsb_tsdf_t *e, int which, int *value);
 
+/* ITMBasicEngine::SaveSceneToMesh (Core/ITMBasicEngine.tpp:105-117) minus the file: marching cubes over every allocated voxel block
+ * (ITMMeshingEngine_*::MeshScene, Engines/Meshing/Shared/ITMMeshingEngine_Shared.h:277-470).  tri_dev: device buffer of max_tri triangles,
+ * 18 floats each = p0 p1 p2 (metres) c0 c1 c2 (0..1), or NULL to count only.  Deterministic, in the CPU mesher's order (ascending hash entry,
+ * z, y, x, case-table order); like the reference at most max_tri - 1 triangles are kept.  *n_tri = triangles written (or present when
+ * tri_dev is NULL).  Synchronises.  gps_slam_b200/checkpoint.py writes the reference's ASCII PLY from it. */
+int gsb_tsdf_mesh(gsb_tsdf_t *e, float *tri_dev, long long max_tri, long long *n_tri);
+
 /* ITMBasicEngine::LoadFromFile (Core/ITMBasicEngine.tpp:137-171) minus the file I/O: resets the engine, then installs the scene from
  * host arrays in the reference's own layouts (hash.dat / voxel.dat payloads, lastFreeBlockId of vba.txt, lastFreeExcessListId of last.txt).
  * SaveToFile is gsb_tsdf_read(GSB_TSDF_HASH_TABLE / GSB_TSDF_VOXELS) + gsb_tsdf_counter(0 / 1); gps_slam_b200/checkpoint.py writes and

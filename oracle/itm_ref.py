@@ -176,6 +176,13 @@ class ItmRef:
         p = self.L.itmref_depth_level(self.h_, level, C.byref(w), C.byref(h))
         return self._arr(p, np.float32, (h.value, w.value))
 
+    def mesh(self, max_tri=4_000_000):
+        """triangles of the reference's marching-cubes export [n, 18] = p0 p1 p2 (metres) c0 c1 c2 (0..1), hash-entry order"""
+        self.L.itmref_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        out = np.zeros((max_tri, 18), np.float32)
+        n = self.L.itmref_mesh(self.h_, out.ctypes.data_as(C.c_void_p), max_tri)
+        return out[:n].copy()
+
     def tracker_result(self):
         return self.L.itmref_tracker_result(self.h_)
 

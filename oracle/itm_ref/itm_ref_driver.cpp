@@ -39,6 +39,9 @@
 #include "ITMLib/Trackers/Interface/ITMDepthTracker.h"
 #include "ITMLib/Trackers/CPU/ITMExtendedTracker_CPU.h"
 #include "ITMLib/Trackers/CPU/ITMDepthTracker_CPU.h"
+#include "ITMLib/Engines/Meshing/CPU/ITMMeshingEngine_CPU.h"
+#include "ITMLib/Engines/Meshing/Shared/ITMMeshingEngine_Shared.h"
+#include "ITMLib/Objects/Meshing/ITMMesh.h"
 #undef private
 #undef protected
 
@@ -79,6 +82,13 @@ void *itmref_create(int w, int h, float fx, float fy, float cx, float cy,
 
 	r->settings = new ITMLibSettings();
 	r->settings->deviceType = ITMLibSettings::DEVICE_CPU;
+#ifndef COMPILE_WITHOUT_CUDA
+	// oracle/itm_ref_cuda builds this same driver with the reference's CUDA engine compiled in: ITMREF_DEVICE=cuda runs it (timing only --
+	// the read-back accessors below return host pointers, which the CUDA engine does not keep up to date)
+	if (const char *d = getenv("ITMREF_DEVICE"))
+		if (!strcmp(d, "cuda"))
+			r->settings->deviceType = ITMLibSettings::DEVICE_CUDA;
+#endif
 	r->settings->createMeshingEngine = false;
 	r->settings->sceneParams.voxelSize = voxelSize;
 	r->settings->sceneParams.mu = mu;
@@ -286,4 +296,50 @@ int itmref_load(void *h, const char *dir)
 	}
 }
 
+
+// SaveSceneToMesh (Core/ITMBasicEngine.tpp:105-117) without the file: the reference's own ITMMeshingEngine_CPU::MeshScene gives the triangle
+// POSITIONS in hash-entry order; it leaves the per-vertex colours unset (only its CUDA twin fills c0..c2, Engines/Meshing/CUDA/
+// ITMMeshingEngine_CUDA.tcu:118-137), so the colours come from a second walk in the same order that calls the reference's buildVertList and
+// takes colorList[] exactly like the CUDA kernel does.  out: [max_tri][18] floats = p0 p1 p2 c0 c1 c2; returns the triangle count.
+int itmref_mesh(void *h, float *out, int max_tri)
+{
+	ItmRef *r = (ItmRef *)h;
+	ITMScene<ITMVoxel, ITMVoxelIndex> *scene = r->engine->scene;
+	ITMMesh mesh(MEMORYDEVICE_CPU, (uint)max_tri);
+	ITMMeshingEngine_CPU<ITMVoxel, ITMVoxelIndex> eng;
+	eng.MeshScene(&mesh, scene);
+	const int n = (int)mesh.noTotalTriangles;
+	const ITMMesh::Triangle *tri = mesh.triangles->GetData(MEMORYDEVICE_CPU);
+	const ITMVoxel *localVBA = scene->localVBA.GetVoxelBlocks();
+	const ITMHashEntry *hashTable = scene->index.GetEntries();
+	int k = 0;
+	for (int entryId = 0; entryId < scene->index.noTotalEntries && k < n; entryId++)
+	{
+		const ITMHashEntry &e = hashTable[entryId];
+		if (e.ptr < 0)
+			continue;
+		Vector3i globalPos = e.pos.toInt() * SDF_BLOCK_SIZE;
+		for (int z = 0; z < SDF_BLOCK_SIZE; z++)
+			for (int y = 0; y < SDF_BLOCK_SIZE; y++)
+				for (int x = 0; x < SDF_BLOCK_SIZE; x++)
+				{
+					Vector3f vertList[12], colorList[12];
+					int cubeIndex = buildVertList(vertList, colorList, globalPos, Vector3i(x, y, z), localVBA, hashTable);
+					if (cubeIndex < 0)
+						continue;
+					for (int i = 0; triangleTable[cubeIndex][i] != -1 && k < n; i += 3, k++)
+					{
+						float *o = out + (size_t)k * 18;
+						const Vector3f *p[3] = {&tri[k].p0, &tri[k].p1, &tri[k].p2};
+						for (int v = 0; v < 3; v++)
+						{
+							o[v * 3 + 0] = p[v]->x, o[v * 3 + 1] = p[v]->y, o[v * 3 + 2] = p[v]->z;
+							const Vector3f &c = colorList[triangleTable[cubeIndex][i + v]];
+							o[9 + v * 3 + 0] = c.x, o[9 + v * 3 + 1] = c.y, o[9 + v * 3 + 2] = c.z;
+						}
+					}
+				}
+	}
+	return n;
+}
 } // extern "C"

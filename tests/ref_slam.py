@@ -179,12 +179,21 @@ def run_both(n_frames, scale=1.0, eval_every=10, device=0, verbose=False):
         pipe = cls(intr, mode="train", device=device, stream=None, overlap=False, gs_capacity=1 << 20)
         counts, spawned = [], []
         if True:
+            import time
+            torch.cuda.synchronize()
+            t_loop = time.perf_counter()
+            t_last10 = t_loop
             for f in range(n_frames):
+                if f == n_frames - 11:
+                    torch.cuda.synchronize()
+                    t_last10 = time.perf_counter()
                 pipe.process_frame(f, rgba, depth, poses, True)
                 if f % 10 == 0 and f > 0:
                     counts.append(pipe.gs.getGaussianNum() if name == "engine" else pipe.n_gauss)
                     spawned.append(pipe.spawned_last)
             torch.cuda.synchronize()
+            t_end = time.perf_counter()
+            loop_s, last_cycle_s = t_end - t_loop, t_end - t_last10
             rgb, dep, alpha = torch.empty((H, W, 3), device=dev), torch.empty((H, W), device=dev), torch.empty((H, W), device=dev)
             ps, imgs = [], []
             for i in range(0, n_frames, eval_every):
@@ -194,7 +203,8 @@ def run_both(n_frames, scale=1.0, eval_every=10, device=0, verbose=False):
                 ps.append(psnr(img, rgba[i][..., :3].float() / 255.0))
                 imgs.append(img)
         res[name] = dict(psnr_db=float(np.mean(ps)), psnr_each=[round(float(p), 3) for p in ps], gaussians_after_each_cycle=counts,
-                         spawned_each_cycle=spawned, last_loss=pipe.last_loss if name != "engine" else pipe.gs.loss())
+                         spawned_each_cycle=spawned, last_loss=pipe.last_loss if name != "engine" else pipe.gs.loss(),
+                         loop_seconds=loop_s, frames_per_sec=n_frames / loop_s, last_cycle_ms=last_cycle_s * 1e3)
         renders[name] = imgs
         pipe.close()
         if verbose:
