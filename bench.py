@@ -137,6 +137,7 @@ def ncu_traffic():
     out = {}
     for name, v in k.items():
         out.setdefault(name.split("::")[-1].split("<")[0], v["dram_bytes_per_launch"])
+        out.setdefault("issue:" + name.split("::")[-1].split("<")[0], v.get("issue_slots_busy_pct"))
     return out, os.path.basename(files[-1])
 
 
@@ -430,6 +431,20 @@ def main():
             if r.get("kernel") in traffic:
                 r["traffic"] = traffic[r["kernel"]]
                 r["traffic_source"] = "profiles/" + src
+                busy = traffic.get("issue:" + r["kernel"])
+                if busy is not None:
+                    # what actually bounds the kernel: the share of the SMs' instruction issue slots it keeps busy (ncu
+                    # sm__inst_issued.avg.pct_of_peak_sustained_active of the committed capture) -- the HBM fraction above is reported
+                    # because the contract asks for it
+                    r["issue_bound"] = {"issue_slots_busy_frac": busy / 100.0, "source": "profiles/" + src}
+        u = roofline.get("units") or {}
+        if u.get("bwd_pairs_tested"):
+            t_bwd = roofline["avg_launch_us"] * 1e-6
+            roofline["pairs"] = {"tested": u["bwd_pairs_tested"], "passed": u["bwd_pairs_passed"],
+                                 "tested_per_visible_gaussian": u["bwd_pairs_tested"] / max(1, u["visible_gaussians"]),
+                                 "pairs_tested_per_second": u["bwd_pairs_tested"] / t_bwd,
+                                 "issue_slots_per_tested_pair": 148 * 4 * 1.965e9 * t_bwd / u["bwd_pairs_tested"],
+                                 "note": "issue slots = 148 SMs x 4 schedulers x 1.965 GHz x kernel time; one slot = one warp instruction (32 lanes)"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(intr, poses, rgba, depth, t0f)

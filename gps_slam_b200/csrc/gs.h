@@ -54,7 +54,9 @@ enum
     CNT_VISIBLE_LAST = 4,
     CNT_SCRATCH = 5,  // prune / spawn scratch (2 ints)
     CNT_BWD_CURSOR = 7, // work-item cursor of the rasteriser backward
-    CNT_TOTAL = 8
+    CNT_PAIRS_TESTED = 8,  // 64-bit (2 ints): (pixel, splat) pairs the statistics build of the rasteriser backward evaluated ...
+    CNT_PAIRS_PASSED = 10, // 64-bit: ... and how many of them passed the alpha / depth tests (gsb_gs_run_stage 6)
+    CNT_TOTAL = 16
 };
 
 struct Bins
@@ -191,6 +193,7 @@ void staged_adam(int n, float *p, const float *g, float *m, float *v, const Adam
 void raster_fwd(int mode, const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
 void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, const float *v_depth /* nullable [H,W] */,
                 SplatGrad *grads, cudaStream_t st);
+void raster_bwd_stats(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, SplatGrad *grads, cudaStream_t st);
 void composite(int mode, const float *acc5 /* [P*4] render then [P] alphas */, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st);
 void raster_fwd_push(const SplatRec *recs, const Bins &bins, int W, int H, int tileW, int tileH, const RasterIO &io, const CommView *cvDev, bool pushAll,
                      cudaStream_t st);

@@ -640,6 +640,10 @@ extern "C" int gsb_gs_run_stage(gsb_gs_t *e, int stage)
         GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), e->stream));
         raster_bwd(e->recs, e->bins, e->W, e->H, e->lastIo, nullptr, e->grads, e->stream);
         break;
+    case 6: // rasteriser backward with pair statistics (GSB_GS_COUNTERS ints 8-11: pairs tested / passed as two 64-bit values)
+        GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_BWD_CURSOR, 0, sizeof(int), e->stream));
+        raster_bwd_stats(e->recs, e->bins, e->W, e->H, e->lastIo, e->grads, e->stream);
+        break;
     case 4: GS_CUDA_OK(cudaMemsetAsync(e->bins.counters + CNT_ITEMS, 0, sizeof(int), e->stream)); break;
     case 5: // parameter backward + Adam with a zero step size (moments advance, parameters do not move)
     {

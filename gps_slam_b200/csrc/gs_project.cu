@@ -791,16 +791,29 @@ __global__ void __launch_bounds__(1024) k_prune_scan(int *chunkCnt, int nChunks,
     }
 }
 
-// copies one Gaussian's row of all six parameter arrays
-__device__ __forceinline__ void copy_param_row(const ParamPtrs &dst, int d, const ParamPtrs &src, int g)
+// Warp-cooperative copy of the kept rows of one parameter array: the warp's 32 source rows (width WIDTH floats, rows g0 .. g0 + 31) shrink to
+// the rows named by `mask`, which land on consecutive destination rows starting at d0 (stable compaction).  Lanes walk the destination run
+// float by float -- coalesced stores, and loads that are contiguous over every kept row -- instead of one strided row per thread.
+// rowSel (optional, per-lane): copy kept row r only if bit r of rowSel is set (moments travel only with Gaussians that have state).
+template <int WIDTH>
+__device__ __forceinline__ void warp_compact_rows(float *__restrict__ dst, const float *__restrict__ src, int g0, int d0, unsigned mask,
+                                                  int srcRowOfKept /* lane r: source row (0..31) of the r-th kept row */, unsigned rowSel)
 {
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        dst.means[d * 3 + i] = src.means[g * 3 + i], dst.scales[d * 3 + i] = src.scales[g * 3 + i], dst.dc[d * 3 + i] = src.dc[g * 3 + i];
-    reinterpret_cast<float4 *>(dst.quats)[d] = reinterpret_cast<const float4 *>(src.quats)[g];
-    dst.opac[d] = src.opac[g];
-    for (int e = 0; e < 45; e++)
-        dst.rest[(size_t)d * 45 + e] = src.rest[(size_t)g * 45 + e];
+    const int lane = threadIdx.x & 31;
+    const int nKept = __popc(mask);
+    const int total = nKept * WIDTH;
+    // lane's float index i = lane + 32 k  ->  (row r, element e); 32 < WIDTH is not required: advance by division-free steps
+    int r = lane / WIDTH, e = lane - r * WIDTH;
+    for (int base = 0; base < total; base += 32)   // warp-uniform trip count: every lane takes part in the shuffle
+    {
+        const int i = base + lane;
+        const int sr = __shfl_sync(0xffffffffu, srcRowOfKept, r & 31);
+        if (i < total && ((rowSel >> (r & 31)) & 1u))
+            dst[(size_t)d0 * WIDTH + i] = src[(size_t)(g0 + sr) * WIDTH + e];
+        e += 32;
+        while (e >= WIDTH)
+            e -= WIDTH, r++;
+    }
 }
 
 // Stable compaction of the survivors: parameters always; the Adam moments and the state flag travel with their Gaussian
@@ -810,21 +823,51 @@ __global__ void __launch_bounds__(1024) k_prune_scatter(PruneBuffers b, const in
                                                          float maxScale, const int *__restrict__ chunkOff)
 {
     __shared__ int ws[33];
-    int g = blockIdx.x * 1024 + threadIdx.x;
-    int nOld = counters[CNT_SCRATCH + 1];
-    int keep = (g < nOld) ? (int)prune_keep(b.p, g, minOpac, minScale, maxScale) : 0;
+    const int g = blockIdx.x * 1024 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int nOld = counters[CNT_SCRATCH + 1];
+    const int keep = (g < nOld) ? (int)prune_keep(b.p, g, minOpac, minScale, maxScale) : 0;
     int total;
-    int ex = block_excl_scan_1024(keep, ws, total);
-    if (!keep)
+    const int ex = block_excl_scan_1024(keep, ws, total);
+    const int d = chunkOff[blockIdx.x] + ex;
+    // per warp: kept mask, first destination row, and for lane r the source row of the r-th kept Gaussian
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (mask == 0)
         return;
-    int d = chunkOff[blockIdx.x] + ex;
-    copy_param_row(b.pOut, d, b.p, g);
-    const unsigned char t = b.touched[g];
-    b.touchedOut[d] = t;
-    if (t)
+    const int d0 = __shfl_sync(0xffffffffu, d, __ffs(mask) - 1);
+    const int srcRow = __fns(mask, 0, lane + 1);   // 0xffffffff beyond the kept count (never selected)
+    const int g0 = g - lane;
+    unsigned char t = keep ? b.touched[g] : 0;
+    if (keep)
+        b.touchedOut[d] = t;
+    // bit r of `sel` = the r-th kept row has optimiser state
+    const unsigned stateOfLane = __ballot_sync(0xffffffffu, t != 0);
+    unsigned sel = 0;
     {
-        copy_param_row(b.mOut, d, b.m, g);
-        copy_param_row(b.vOut, d, b.v, g);
+        const int has = srcRow >= 0 && srcRow < 32 && ((stateOfLane >> srcRow) & 1u);
+        sel = __ballot_sync(0xffffffffu, has);
+    }
+    const unsigned all = 0xffffffffu;
+    warp_compact_rows<3>(b.pOut.means, b.p.means, g0, d0, mask, srcRow, all);
+    warp_compact_rows<3>(b.pOut.scales, b.p.scales, g0, d0, mask, srcRow, all);
+    warp_compact_rows<4>(b.pOut.quats, b.p.quats, g0, d0, mask, srcRow, all);
+    warp_compact_rows<3>(b.pOut.dc, b.p.dc, g0, d0, mask, srcRow, all);
+    warp_compact_rows<45>(b.pOut.rest, b.p.rest, g0, d0, mask, srcRow, all);
+    warp_compact_rows<1>(b.pOut.opac, b.p.opac, g0, d0, mask, srcRow, all);
+    if (sel)
+    {
+        warp_compact_rows<3>(b.mOut.means, b.m.means, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<3>(b.mOut.scales, b.m.scales, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<4>(b.mOut.quats, b.m.quats, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<3>(b.mOut.dc, b.m.dc, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<45>(b.mOut.rest, b.m.rest, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<1>(b.mOut.opac, b.m.opac, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<3>(b.vOut.means, b.v.means, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<3>(b.vOut.scales, b.v.scales, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<4>(b.vOut.quats, b.v.quats, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<3>(b.vOut.dc, b.v.dc, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<45>(b.vOut.rest, b.v.rest, g0, d0, mask, srcRow, sel);
+        warp_compact_rows<1>(b.vOut.opac, b.v.opac, g0, d0, mask, srcRow, sel);
     }
 }
 

@@ -240,13 +240,19 @@ __device__ __forceinline__ float halfwarp_reduce16(float (&v)[16], int lane)
 // half-warp reduction and one store (or 10 atomics when the splat has several items).  Compared with a whole warp per item this
 // halves the per-item overhead (record loads, rectangle setup, reduction) and wastes fewer lanes on the typical 100-200 pixel
 // rectangles.  HAS_VD: a depth-channel gradient image is supplied (depth_weight > 0; off in every release config).
-template <bool HAS_VD>
+// (A quarter warp per item -- four items side by side, so that the ~450 instructions a warp spends per batch of items outside the pixel
+// loop are shared by four items instead of two -- was built and measured: 336 us against 294 us.  The warp runs for as long as its
+// longest item, and four neighbours differ more than two.)
+template <bool HAS_VD, bool STATS = false>
 __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restrict__ recs, const int4 *__restrict__ items, int *counters, int itemCap,
                                                         int W, const float4 *__restrict__ v_out, const float *__restrict__ v_depthImg,
                                                         SplatGrad *__restrict__ grads)
 {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    constexpr int LPI = 16;          // lanes per item
+    constexpr int IPW = 32 / LPI;    // items per warp
+    constexpr int PXS = 2 * LPI;     // rect-linear pixels of one item per step
+    const int lane = threadIdx.x & 31, hl = lane & (LPI - 1), half = lane / LPI;
     const int nItems = min(counters[CNT_ITEMS], itemCap);
     // dynamic distribution of work items over the resident warps: items differ by up to 64x in cost
     int *cursor = counters + CNT_BWD_CURSOR;
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
         }
         const int mine = it + half;
         const bool live = mine < itEnd;
-        it += 2;
+        it += IPW;
         const int4 item = __ldg(&items[live ? mine : itEnd - 1]);
         const int g = item.x;
         const float4 q0 = __ldg(&recs[g].q0), q1 = __ldg(&recs[g].q1), q2 = __ldg(&recs[g].q2);
@@ -279,9 +285,9 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
         const float inv_rw = 1.0f / (float)rw;
         const int p0 = item.y;
         const int p1 = live ? min(p0 + BWD_PIXELS_PER_ITEM, npix) : p0;
-        // Each lane walks two pixel sequences, ids p0 + hl + 32 k and p0 + 16 + hl + 32 k, in rect-linear order.  Pixel centre
-        // (px, py) and image index are advanced incrementally: +32 ids = +q32 rows, +r32 columns with at most one wrap.
-        const int q32 = (int)(32.5f * inv_rw), r32 = 32 - q32 * rw; // exact: rw <= 200
+        // Each lane walks two pixel sequences, ids p0 + hl + PXS k and p0 + LPI + hl + PXS k, in rect-linear order.  Pixel centre
+        // (px, py) and image index are advanced incrementally: +PXS ids = +q32 rows, +r32 columns with at most one wrap.
+        const int q32 = (int)(((float)PXS + 0.5f) * inv_rw), r32 = PXS - q32 * rw; // exact: rw <= 200
         const float r32f = (float)r32, q32f = (float)q32, rwf = (float)rw;
         const float xEnd = (float)(rx + rw);                       // first pixel centre beyond the rect is xEnd + 0.5
         const int dpix = q32 * W + r32, dwrap = W - rw;
@@ -290,18 +296,19 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
 #pragma unroll
         for (int u = 0; u < 2; u++)
         {
-            const int id = p0 + u * 16 + hl;
+            const int id = p0 + u * LPI + hl;
             const int row = (int)(((float)id + 0.5f) * inv_rw); // exact for id < 2^16, rw <= 200
             const int col = id - row * rw;
             px[u] = (float)(rx + col) + 0.5f, py[u] = (float)(ry + row) + 0.5f;
             pix[u] = (ry + row) * W + rx + col;
         }
-        // steps of the longer of the two items
-        int steps = (p1 - p0 + 31) >> 5;
+        // steps of the longest of the warp's items
+        int steps = (p1 - p0 + PXS - 1) / PXS;
         steps = max(steps, __shfl_xor_sync(full, steps, 16));
         // gradient sums; the conic / mean gradients are accumulated as moments of t = v_sigma over (dx, dy):
         // v_conic = (Sxx/2, Sxy, Syy/2), v_mean2d = (a Sx + b Sy, b Sx + c Sy)
         float vr = 0.f, vg = 0.f, vb = 0.f, vd = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, sx = 0.f, sy = 0.f, vo = 0.f;
+        int nTested = 0, nPassed = 0; // STATS build only
         // Per-pixel record of the backward: 32 bytes = (dL/d render rgb, dL/d alpha | depth cut, -, -, -), written by the forward, so one
         // address serves both reads.  Software pipeline, unrolled by two so that the in-flight buffers alternate without register
         // copies: the reads of step k+1 are issued, unconditionally for every pixel of the rectangle, before the arithmetic of step k.
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
             {
                 d.dx[u] = q0.x - px[u], d.dy[u] = q0.y - py[u];
                 d.cut[u] = -1e30f, d.vdp[u] = 0.f, d.vo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idBase + u * 16 < p1)
+                if (idBase + u * LPI < p1)
                 {
                     const float4 *rec = v_out + 2 * (size_t)pix[u];
                     d.vo[u] = __ldg(rec);
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
                     if (HAS_VD)
                         d.vdp[u] = __ldg(&v_depthImg[pix[u]]);
                 }
-                // advance to the pixel 32 ids further
+                // advance to the pixel PXS ids further
                 px[u] += r32f, py[u] += q32f, pix[u] += dpix;
                 if (px[u] > xEnd)
                     px[u] -= rwf, py[u] += 1.0f, pix[u] += dwrap;
@@ -343,8 +350,12 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
                 const float ar = opac * vis;
                 const float alpha = fminf(0.999f, ar);
                 // (pixels beyond the item carry cut = -1e30 and fail the depth test)
+                if (STATS)
+                    nTested += d.cut[u] > -1e29f;
                 if (s2 < 0.f || alpha < 1.f / 255.f || q1.w > d.cut[u])
                     continue;
+                if (STATS)
+                    nPassed++;
                 const float4 vo4 = d.vo[u];
                 vr += alpha * vo4.x;
                 vg += alpha * vo4.y;
@@ -371,11 +382,11 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
         };
         PixData dA, dB;
         fetch(dA, id0);
-        for (int k = 0; k < steps; k += 2, id0 += 64)
+        for (int k = 0; k < steps; k += 2, id0 += 2 * PXS)
         {
-            fetch(dB, id0 + 32);
+            fetch(dB, id0 + PXS);
             consume(dA);
-            fetch(dA, id0 + 64);
+            fetch(dA, id0 + 2 * PXS);
             consume(dB); // (a step beyond `steps` only sees pixels beyond the item: nothing passes)
         }
         // slots follow the float layout of SplatGrad: (vx, vy, vo, vd | vca, vcb, vcc, - | vr, vg, vb, -)
@@ -385,6 +396,16 @@ __global__ void __launch_bounds__(256, 3) k_raster_bwd(const SplatRec *__restric
         v16[8] = vr, v16[9] = vg, v16[10] = vb, v16[11] = 0.f;
         v16[12] = v16[13] = v16[14] = v16[15] = 0.f;
         const float total = halfwarp_reduce16(v16, lane);
+        if (STATS)
+        {
+            for (int o = 16; o; o >>= 1)
+                nTested += __shfl_xor_sync(full, nTested, o), nPassed += __shfl_xor_sync(full, nPassed, o);
+            if (lane == 0)
+            {
+                atomicAdd(reinterpret_cast<unsigned long long *>(counters + CNT_PAIRS_TESTED), (unsigned long long)nTested);
+                atomicAdd(reinterpret_cast<unsigned long long *>(counters + CNT_PAIRS_PASSED), (unsigned long long)nPassed);
+            }
+        }
         if (live && hl < 11 && hl != 7)
         {
             float *f = reinterpret_cast<float *>(grads + g) + hl;
@@ -624,6 +645,15 @@ void raster_bwd(const SplatRec *recs, const Bins &bins, int W, int H, const Rast
         k_raster_bwd<true><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.v_out, v_depth, grads);
     else
         k_raster_bwd<false><<<grid, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.v_out, nullptr, grads);
+}
+
+// the same kernel with its pair counters compiled in (measurement aid: how many (pixel, splat) pairs the backward evaluates and how many
+// pass -- counters[CNT_PAIRS_TESTED / CNT_PAIRS_PASSED], zeroed here)
+void raster_bwd_stats(const SplatRec *recs, const Bins &bins, int W, int H, const RasterIO &io, SplatGrad *grads, cudaStream_t st)
+{
+    GS_COUNT_LAUNCHES(1);
+    cudaMemsetAsync(bins.counters + CNT_PAIRS_TESTED, 0, 4 * sizeof(int), st);
+    k_raster_bwd<false, true><<<148 * 3, 256, 0, st>>>(recs, bins.items, bins.counters, bins.itemCap, W, io.v_out, nullptr, grads);
 }
 
 void composite(int mode, const float *acc5, int W, int H, int tileW, int tileH, const RasterIO &io, cudaStream_t st)

@@ -592,6 +592,14 @@ class GaussianEngine:
     def counters(self):
         return self.read(GS_COUNTERS, np.int32, (8,))
 
+    def bwd_pair_stats(self):
+        """(pixel, splat) pairs the rasteriser backward evaluates / that pass its tests, for the work list of the last train step
+        (run_stage 6: the backward kernel with its counters compiled in)"""
+        self.run_stage(6)
+        c = self.read(GS_COUNTERS, np.int32, (16,))
+        t = c[8:12].view(np.uint64)
+        return int(t[0]), int(t[1])
+
     def splat_records(self, n):
         r = self.read(GS_SPLAT_RECORDS, np.float32, (n, 12))
         radii = r[:, 3].copy().view(np.int32)

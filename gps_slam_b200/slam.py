@@ -543,6 +543,10 @@ class SlamPipeline:
         table["gs_bwd_params+adam_rest(2 kernels)"] = t15 - table["gs_project_sh+bin_tiles(4 kernels)"]
         with torch.cuda.stream(stream):
             g.run_stage(4)
+        with torch.cuda.stream(stream):
+            g.run_stage(1)          # a fresh work list for the pair statistics of the backward
+            pairs_tested, pairs_passed = g.bwd_pair_stats()
+            g.run_stage(4)
         table["gs_train_step(7 kernels, no flush)"] = self._time(
             stream, lambda: g.train_step(cam.c2w_slam, self.intr, cam.depth_map, cam.color_map, cam.image), reps, flush) * 1e6
         if self.comm is not None and self.world > 1:
@@ -564,5 +568,6 @@ class SlamPipeline:
         ach = alg / t / 1e9
         return {"kernel": "k_raster_bwd", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
                 "traffic": None, "algorithmic_bytes": alg, "avg_launch_us": t * 1e6,
-                "units": {"pixels": P, "isects": I, "visible_gaussians": n_vis, "gaussians": self.n_gauss},
+                "units": {"pixels": P, "isects": I, "visible_gaussians": n_vis, "gaussians": self.n_gauss,
+                          "bwd_pairs_tested": pairs_tested, "bwd_pairs_passed": pairs_passed},
                 "kernels_us": table, "step_breakdown": self.breakdown, "tsdf_integrate": integrate}

@@ -370,14 +370,15 @@ enum
     GSB_GS_TILE_OFFSETS = 2,    /* int[T+1]  (isect_offsets + n_isects)                                                  */
     GSB_GS_FLATTEN_IDS = 3,     /* int[n_isects]                                                                         */
     GSB_GS_V_OUT = 4,           /* 8 floats per pixel [H*W]: dL/d render rgb, dL/d alpha | depth cut, 3 x padding        */
-    GSB_GS_COUNTERS = 5,        /* int[8]: n_isects, n_items, overflow bits, -, n_visible, ...                           */
+    GSB_GS_COUNTERS = 5,        /* int[16]: n_isects, n_items, overflow bits, -, n_visible, ...; [8..11] pair statistics of stage 6 */
     GSB_GS_GRAD_MEANS = 6, GSB_GS_GRAD_SCALES = 7, GSB_GS_GRAD_QUATS = 8, GSB_GS_GRAD_DC = 9, GSB_GS_GRAD_REST = 10, GSB_GS_GRAD_OPAC = 11,
     GSB_GS_SPAWN_PIXELS = 12    /* int[<= H*W]: pixel index of every Gaussian the last gsb_gs_spawn appended, in append order      */
 };
 int gsb_gs_read(gsb_gs_t *e, int what, void *dst_host, size_t bytes);
 /* single stages on the camera / images of the last train step, for per-kernel timing: 0 projection+SH, 1 tile binning,
  * (1 re-runs 0), 2 rasteriser forward (train), 3 rasteriser backward, 4 drop the backward work list (call last),
- * 5 parameter backward + Adam with a zero step size (consumes the work list) */
+ * 5 parameter backward + Adam with a zero step size (consumes the work list), 6 rasteriser backward with its pair counters compiled in
+ * ((pixel, splat) pairs evaluated / passed -> GSB_GS_COUNTERS[8..11], two 64-bit values) */
 int gsb_gs_run_stage(gsb_gs_t *e, int stage);
 int gsb_gs_enable_grad_dump(gsb_gs_t *e, int on);   /* keep the parameter gradients of each train step for GSB_GS_GRAD_* */
 
