@@ -325,8 +325,16 @@ def main():
     rgba_h = torch.empty((t1f - w0,) + tuple(rgba.shape[1:]), dtype=rgba.dtype, pin_memory=True).copy_(rgba[w0:t1f])
     depth_h = torch.empty((t1f - w0,) + tuple(depth.shape[1:]), dtype=depth.dtype, pin_memory=True).copy_(depth[w0:t1f])
     stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("GSB_MAIN_STREAM_PRIORITY", "-1")))
-    pipe = slam.SlamPipeline(intr, mode=mode, device=local, stream=stream, rank=rank, world=world, use_gt_pose=track == 0,
-                             tracker=track or 1, gs_capacity=int(os.environ.get("GSB_GS_CAPACITY", str(1 << 22))))
+    # world >= 4: functional split (gps_slam_b200/split.py: rank 0 = the TSDF side, the others = Gaussian shards) unless GSB_SPLIT=0;
+    # otherwise every rank runs both sides, Gaussians / voxel hash / ICP sharded
+    split = world >= 4 and track == 0 and mode == "train" and os.environ.get("GSB_SPLIT", "1") != "0"
+    if split:
+        from gps_slam_b200 import split as split_mod
+        pipe = split_mod.SplitSlamPipeline(intr, device=local, stream=stream, rank=rank, world=world,
+                                           gs_capacity=int(os.environ.get("GSB_GS_CAPACITY", str(1 << 22))))
+    else:
+        pipe = slam.SlamPipeline(intr, mode=mode, device=local, stream=stream, rank=rank, world=world, use_gt_pose=track == 0,
+                                 tracker=track or 1, gs_capacity=int(os.environ.get("GSB_GS_CAPACITY", str(1 << 22))))
 
     def barrier():
         if world > 1:
@@ -406,6 +414,10 @@ def main():
                          "raise gs_capacity / isect_capacity / item_capacity" % stats["overflow_flags"])
     full_run.update(gaussians_final=stats.get("gaussians"), allocated_blocks_final=stats.get("allocated_blocks"), overflow_flags=stats.get("overflow_flags", 0))
     psnr = eval_psnr(pipe, intr, poses, rgba, list(range(0, total, 40)), dev) if mode == "train" else None
+    if psnr is not None and split:
+        got = [None] * world     # the renders exist on the Gaussian ranks: rank 1's figures are the record
+        dist.all_gather_object(got, psnr)
+        psnr = got[1]
     if psnr is not None:
         ref_rec = psnr_vs_reference()
         psnr["psnr_vs_reference_db"] = ref_rec["psnr_vs_reference_db"] if ref_rec else None

@@ -26,6 +26,7 @@ SOURCES = [
     ("gs_ssim.cu", []),
     ("gs_knn.cu", []),
     ("gs_comm.cu", []),
+    ("peer_mbox.cu", []),
     ("gs_engine.cu", ["-fmad=false"]),
 ]
 

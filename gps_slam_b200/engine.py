@@ -145,6 +145,18 @@ def load_library():
     L.gsb_comm_destroy.argtypes = [vp]
     L.gsb_comm_destroy.restype = None
     L.gsb_gs_set_comm.argtypes = [vp, vp]
+    L.gsb_mbox_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.gsb_mbox_export.argtypes = [vp, vp]
+    L.gsb_mbox_attach.argtypes = [vp, vp]
+    L.gsb_mbox_attach_local.argtypes = [vp, C.POINTER(vp)]
+    L.gsb_mbox_local.argtypes = [vp]
+    L.gsb_mbox_local.restype = vp
+    L.gsb_mbox_put.argtypes = [vp, C.c_int, C.c_size_t, vp, C.c_size_t, vp]
+    L.gsb_mbox_signal.argtypes = [vp, C.c_int, C.c_int, C.c_uint, vp]
+    L.gsb_mbox_wait.argtypes = [vp, C.c_int, C.c_uint, vp]
+    L.gsb_mbox_error.argtypes = [vp]
+    L.gsb_mbox_destroy.argtypes = [vp]
+    L.gsb_mbox_destroy.restype = None
     L.gsb_gs_raycast_maps.argtypes = [vp, vp, vp, vp, fl, vp, vp, vp]
     L.gsb_gs_frame_to_float.argtypes = [vp, vp, vp, vp, vp]
     L.gsb_tsdf_current_rgba_dev.argtypes = [vp]
@@ -419,6 +431,52 @@ class PeerComm:
     def close(self):
         if self.h_:
             self.L.gsb_comm_destroy(self.h_)
+            self.h_ = None
+
+
+class PeerMailbox:
+    """gsb_mbox_t: a byte segment per rank that the other ranks write into over NVLink + counters for stream hand-shakes
+    (csrc/peer_mbox.cu).  export_handle() / attach(handles) between processes, attach_local(list) inside one process."""
+
+    def __init__(self, device, rank, world, nbytes):
+        self.L = load_library()
+        self.rank, self.world, self.nbytes = rank, world, nbytes
+        h = C.c_void_p()
+        _check(self.L.gsb_mbox_create(device, rank, world, nbytes, C.byref(h)))
+        self.h_ = h
+
+    def export_handle(self):
+        buf = C.create_string_buffer(64)
+        _check(self.L.gsb_mbox_export(self.h_, buf))
+        return buf.raw
+
+    def attach(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        _check(self.L.gsb_mbox_attach(self.h_, C.c_char_p(blob)))
+
+    def attach_local(self, boxes):
+        arr = (C.c_void_p * self.world)(*[b.h_ for b in boxes])
+        _check(self.L.gsb_mbox_attach_local(self.h_, arr))
+
+    def local_ptr(self):
+        return int(self.L.gsb_mbox_local(self.h_))
+
+    def put(self, dst_rank, dst_offset, src, nbytes, cuda_stream_ptr):
+        _check(self.L.gsb_mbox_put(self.h_, dst_rank, dst_offset, _ptr(src), nbytes, C.c_void_p(cuda_stream_ptr)))
+
+    def signal(self, dst_rank, flag, value, cuda_stream_ptr):
+        _check(self.L.gsb_mbox_signal(self.h_, dst_rank, flag, value & 0xffffffff, C.c_void_p(cuda_stream_ptr)))
+
+    def wait(self, flag, value, cuda_stream_ptr):
+        _check(self.L.gsb_mbox_wait(self.h_, flag, value & 0xffffffff, C.c_void_p(cuda_stream_ptr)))
+
+    def error(self):
+        return int(self.L.gsb_mbox_error(self.h_))
+
+    def close(self):
+        if self.h_:
+            self.L.gsb_mbox_destroy(self.h_)
             self.h_ = None
 
 

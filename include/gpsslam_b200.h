@@ -382,6 +382,26 @@ int gsb_gs_read(gsb_gs_t *e, int what, void *dst_host, size_t bytes);
 int gsb_gs_run_stage(gsb_gs_t *e, int stage);
 int gsb_gs_enable_grad_dump(gsb_gs_t *e, int on);   /* keep the parameter gradients of each train step for GSB_GS_GRAD_* */
 
+/* ===================================================================================================
+ * Peer mailbox (new; multi-GPU host plumbing below the C ABI).  A byte segment per rank that every other rank of the box can write into
+ * over NVLink, and 256 counters per rank for hand-shakes on streams.  The functional split of the SLAM loop uses it: the rank that owns
+ * the TSDF side stores the camera maps of a cycle into the Gaussian ranks' mailboxes (gps_slam_b200/split.py).  Mapping as for gsb_comm_*.
+ * =================================================================================================== */
+typedef struct gsb_mbox gsb_mbox_t;
+int gsb_mbox_create(int device, int rank, int world, size_t bytes, gsb_mbox_t **out);
+int gsb_mbox_export(gsb_mbox_t *m, void *handle64);
+int gsb_mbox_attach(gsb_mbox_t *m, const void *handles /* world x 64 bytes */);
+int gsb_mbox_attach_local(gsb_mbox_t *m, gsb_mbox_t *const *peers);
+void *gsb_mbox_local(gsb_mbox_t *m);   /* device pointer of this rank's own mailbox */
+/* enqueue on `stream`: copy bytes from src_dev (this rank) to offset dst_offset of rank dst_rank's mailbox */
+int gsb_mbox_put(gsb_mbox_t *m, int dst_rank, size_t dst_offset, const void *src_dev, size_t bytes, void *stream);
+/* enqueue on `stream`: after everything queued before, counter `flag` of rank dst_rank becomes `value` (release at system scope) */
+int gsb_mbox_signal(gsb_mbox_t *m, int dst_rank, int flag, unsigned value, void *stream);
+/* enqueue on `stream`: the stream proceeds when this rank's counter `flag` has reached `value` (bounded spin -> gsb_mbox_error) */
+int gsb_mbox_wait(gsb_mbox_t *m, int flag, unsigned value, void *stream);
+int gsb_mbox_error(gsb_mbox_t *m);
+void gsb_mbox_destroy(gsb_mbox_t *m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(n_frames, scale, world, rank, local, track=0):
+def run(n_frames, scale, world, rank, local, track=0, split=0):
     import hashlib
     import numpy as np
     import torch
@@ -23,8 +23,13 @@ def run(n_frames, scale, world, rank, local, track=0):
     for i in range(n_frames):
         rgba[i], depth[i] = syn.render_frame(poses[i], intr, device=dev)
     stream = torch.cuda.Stream(device=dev)
-    pipe = slam.SlamPipeline(intr, mode="train", device=local, stream=stream, rank=rank, world=world, gs_capacity=1 << 19,
-                             use_gt_pose=track == 0, tracker=track or 1)
+    if split:
+        # functional split (gps_slam_b200/split.py): rank 0 = the TSDF side, ranks 1.. = Gaussian shards; results live on rank 1
+        from gps_slam_b200 import split as split_mod
+        pipe = split_mod.SplitSlamPipeline(intr, device=local, stream=stream, rank=rank, world=world, gs_capacity=1 << 19)
+    else:
+        pipe = slam.SlamPipeline(intr, mode="train", device=local, stream=stream, rank=rank, world=world, gs_capacity=1 << 19,
+                                 use_gt_pose=track == 0, tracker=track or 1)
     with torch.cuda.stream(stream):
         for f in range(n_frames):
             pipe.process_frame(f, rgba, depth, poses, True)
@@ -38,6 +43,14 @@ def run(n_frames, scale, world, rank, local, track=0):
             mse = float(((rgb.clamp(0, 1) - rgba[i][..., :3].float() / 255.0) ** 2).mean())
             ps.append(20.0 * np.log10(1.0 / np.sqrt(mse)))
     st = pipe.stats()
+    if split:
+        import torch.distributed as dist
+        mine = dict(world=world, loss=pipe.last_loss, gaussians=st["gaussians"], psnr=ps, overflow=st["overflow_flags"],
+                    gaussians_this_rank=st["gaussians_this_rank"], mailbox_errors=st["mailbox_errors"], cycles=st["cycles"])
+        got = [None] * world
+        dist.all_gather_object(got, mine)
+        pipe.close()
+        return dict(got[1], ranks=[g["gaussians_this_rank"] for g in got])
     # TSDF side: replicated state and the last free-view render (every rank holds all rows; sharded: marched by all ranks, voxels read
     # from their owners over NVLink) -- must be bit-identical to the single-GPU run when the poses are given
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
@@ -56,7 +69,8 @@ if __name__ == "__main__":
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    res = run(int(sys.argv[2]), float(sys.argv[3]), world, rank, local, int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+    res = run(int(sys.argv[2]), float(sys.argv[3]), world, rank, local, int(sys.argv[4]) if len(sys.argv) > 4 else 0,
+              int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     if rank == 0:
         with open(sys.argv[1], "w") as f:
             json.dump(res, f)

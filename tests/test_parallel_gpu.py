@@ -59,3 +59,26 @@ def test_two_ranks_track_like_one(engine_lib, tmp_path):
     t1, t2 = one["tracking"], two["tracking"]
     assert t2["frames"] == t1["frames"] and t2["ate_rmse_m"] < 5e-3 and abs(t2["ate_rmse_m"] - t1["ate_rmse_m"]) < 1e-3, (t1, t2)
     assert abs(t2["icp_evaluations_per_frame"] - t1["icp_evaluations_per_frame"]) < 3.0, (t1, t2)
+
+
+def test_functional_split_matches_one(engine_lib, tmp_path):
+    """the functional split (gps_slam_b200/split.py): rank 0 owns the TSDF side and stores the camera maps of every cycle into the other
+    ranks' mailboxes over NVLink, ranks 1-3 hold the Gaussian shards.  The TSDF maps are the single-GPU engine's bit for bit, so the run must
+    end at the single-GPU loss, Gaussian count and PSNR up to the re-association of the summed image (as test_two_ranks_match_one)"""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    from tests import mp_slam_worker
+    n_frames, scale = 31, 0.5
+    out = str(tmp_path / "w4s.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1", "--master-port", "29735",
+           os.path.join(ROOT, "tests", "mp_slam_worker.py"), out, str(n_frames), str(scale), "0", "1"]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-12000:]
+    four = json.load(open(out))
+    one = mp_slam_worker.run(n_frames, scale, 1, 0, 0)
+    assert four["overflow"] == 0 and four["mailbox_errors"] == 0 and four["cycles"] == 3
+    assert four["ranks"][0] == 0 and min(four["ranks"][1:]) > 0.15 * four["gaussians"], four["ranks"]     # three real shards, none on the TSDF rank
+    assert abs(four["gaussians"] - one["gaussians"]) <= 0.005 * one["gaussians"] + 2, (four["gaussians"], one["gaussians"])
+    assert abs(four["loss"] - one["loss"]) <= 2e-3 * one["loss"], (four["loss"], one["loss"])
+    assert np.abs(np.array(four["psnr"]) - np.array(one["psnr"])).max() < 0.05, (four["psnr"], one["psnr"])
