@@ -81,3 +81,22 @@ def test_partial_images_allreduce_to_the_full_image_gloo():
     assert total == 400
     # sums are re-associated across ranks: fp32 tolerance, not bit-exact
     assert d_render < 2e-5 and d_alpha < 2e-5 and d_rgb < 2e-5, res
+
+
+def test_voxel_block_owner_is_a_balanced_partition():
+    """host mirror of the TSDF block-ownership rule (owner = hashIndex(blockPos) mod world, csrc/tsdf.h block_owner): every block has exactly
+    one owner in range, the rule is the reference's hash (ITMRepresentationAccess.h:7-11) folded to 20 bits, and a room-sized set of blocks
+    spreads evenly over 2 ... 8 ranks"""
+    import numpy as np
+    from gps_slam_b200 import parallel
+    rng = np.random.RandomState(3)
+    blocks = rng.randint(-200, 200, size=(50000, 3))
+    h = ((blocks[:, 0].astype(np.int64) * 73856093) ^ (blocks[:, 1].astype(np.int64) * 19349669) ^ (blocks[:, 2].astype(np.int64) * 83492791)) & 0xfffff
+    for world in (1, 2, 3, 4, 8):
+        own = parallel.voxel_block_owner(blocks, world)
+        assert own.min() >= 0 and own.max() < world
+        assert np.array_equal(own, h % world)
+        counts = np.bincount(own, minlength=world)
+        assert counts.min() > 0.9 * len(blocks) / world, counts
+    # negative coordinates hash like the device's 32-bit unsigned arithmetic
+    assert parallel.voxel_block_owner(np.array([[-1, -1, -1]]), 7)[0] == (((-73856093) & 0xffffffff) ^ ((-19349669) & 0xffffffff) ^ ((-83492791) & 0xffffffff)) % (1 << 20) % 7
