@@ -143,8 +143,11 @@ extern "C" int gsb_tsdf_create_sharded(const gsb_tsdf_config_t *cfg, int rank, i
     if (!e)
         return gs_set_error(__FILE__, __LINE__, "out of host memory");
     e->cfg = *cfg;
-    if (const char *v = getenv("GSB_INTEGRATE_VARIANT"))   // experiments: override the integrate kernel variant of every engine
-        e->cfg.integrate_variant = atoi(v);
+    if (e->cfg.integrate_variant != 0)
+    {
+        delete e;
+        return gs_set_error(__FILE__, __LINE__, "integrate_variant must be 0 (the TMA-pipelined kernel; the alternates were removed)");
+    }
     if (e->cfg.num_blocks <= 0)
         e->cfg.num_blocks = SDF_DEFAULT_BLOCK_NUM;
     if (e->cfg.max_w <= 0)

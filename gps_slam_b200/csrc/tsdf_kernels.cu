@@ -663,163 +663,10 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate_tma(Voxel *__restrict
         tma_store_wait_all();
 }
 
-// Warp-specialised variant of the same pipeline (integrate_variant 2).  In k_integrate_tma all 8 warps meet at two CTA barriers per voxel
-// block, and a block's expensive voxels (inside the truncation band, colour update) sit in a few of its z-slices, i.e. in a few warps: ncu
-// attributes 23 % of the stall samples to those barriers.  Here a ninth warp is the producer -- descriptors, TMA loads, TMA write-back --
-// and the eight consumer warps never wait for each other: a consumer waits for the load of its block (full[s]), updates its 64 voxels and
-// arrives on done[s]; the producer retires a stage when all eight have arrived.  With 4 stages a fast warp runs up to 3 blocks ahead of a
-// slow one, so the imbalance averages out over consecutive blocks.  Same voxel arithmetic, same results.
-constexpr int WS_CONSUMERS = 8;
-constexpr int WS_THREADS = (WS_CONSUMERS + 1) * 32;
-constexpr int WS_STAGES = 4;
-constexpr int WS_DESC = 64; // descriptor ring, refilled 32 at a time by the producer warp
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__global__ void __launch_bounds__(WS_THREADS, 4) k_integrate_ws(Voxel *__restrict__ vba, const HashEntry *__restrict__ table,
-                                                                 const int *__restrict__ visIds, const int *__restrict__ nVis,
-                                                                 IntegrateParams P, const float *__restrict__ depth,
-                                                                 const uchar4 *__restrict__ rgb)
-{
-    __shared__ __align__(128) uint2 buf[WS_STAGES][SDF_BLOCK_SIZE3];
-    __shared__ __align__(8) unsigned long long full[WS_STAGES], done[WS_STAGES];
-    __shared__ int sDirty[WS_STAGES];
-    __shared__ int dPtr[WS_DESC];
-    __shared__ short4 dPos[WS_DESC];
-    __shared__ float sRcp[257];
-
-    const int n = *nVis;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 257; i += WS_THREADS)
-        sRcp[i] = c_rcpInt[i];
-    if (tid == 0)
-    {
-        for (int s = 0; s < WS_STAGES; s++)
-        {
-            mbar_init(&full[s], 1);
-            mbar_init(&done[s], WS_CONSUMERS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int myCount = (n > (int)blockIdx.x) ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-
-    if (warp == WS_CONSUMERS)
-    {
-        // ---- producer warp
-        auto retire = [&](int kp) {
-            // lane 0: block kp has been updated by all consumers -> write it back if any voxel changed, and wait until the copy has
-            // finished reading the stage (the next load overwrites it)
-            const int s = kp % WS_STAGES;
-            mbar_wait(&done[s], (unsigned)((kp / WS_STAGES) & 1));
-            const int ptr = dPtr[kp % WS_DESC];
-            if (ptr >= 0 && sDirty[s])
-            {
-                tma_store_1d(vba + (size_t)ptr * SDF_BLOCK_SIZE3, &buf[s][0], SDF_BLOCK_SIZE3 * 8);
-                tma_store_commit();
-                tma_store_wait_read<0>();
-            }
-        };
-        for (int kn = 0; kn < myCount; kn++)
-        {
-            if ((kn & 31) == 0)
-            {
-                // descriptors of blocks kn .. kn+31 (they replace those of blocks kn-64 .. kn-33, all retired by now)
-                const int k = kn + lane;
-                if (k < myCount)
-                {
-                    const int slot = __ldg(&visIds[blockIdx.x + k * gridDim.x]);
-                    const HashEntry e = load_entry(table, slot);
-                    dPtr[k % WS_DESC] = e.ptr;
-                    dPos[k % WS_DESC] = make_short4(e.px, e.py, e.pz, 0);
-                }
-                __syncwarp();
-            }
-            if (lane == 0)
-            {
-                const int s = kn % WS_STAGES;
-                if (kn >= WS_STAGES)
-                    retire(kn - WS_STAGES);
-                sDirty[s] = 0;
-                const int ptr = dPtr[kn % WS_DESC];
-                if (ptr >= 0)
-                {
-                    mbar_expect_tx(&full[s], SDF_BLOCK_SIZE3 * 8);
-                    tma_load_1d(&buf[s][0], vba + (size_t)ptr * SDF_BLOCK_SIZE3, SDF_BLOCK_SIZE3 * 8, &full[s]);
-                }
-                else
-                    mbar_expect_tx(&full[s], 0); // nothing to load: complete the phase so stage parity stays in step
-            }
-            __syncwarp();
-        }
-        if (lane == 0)
-        {
-            for (int kp = max(0, myCount - WS_STAGES); kp < myCount; kp++)
-                retire(kp);
-            tma_store_wait_all();
-        }
-        return;
-    }
-
-    // ---- consumer warps: 256 threads, two voxels each, no CTA-wide synchronisation
-    for (int k = 0; k < myCount; k++)
-    {
-        const int s = k % WS_STAGES;
-        mbar_wait(&full[s], (unsigned)((k / WS_STAGES) & 1));
-        const int ptr = dPtr[k % WS_DESC];
-        if (ptr >= 0)
-        {
-            const short4 bp = dPos[k % WS_DESC];
-            const int gx0 = (int)bp.x * SDF_BLOCK_SIZE, gy0 = (int)bp.y * SDF_BLOCK_SIZE, gz0 = (int)bp.z * SDF_BLOCK_SIZE;
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < SDF_BLOCK_SIZE3 / (WS_CONSUMERS * 32); j++)
-            {
-                const int loc = tid + j * (WS_CONSUMERS * 32);
-                const int z = loc >> 6, y = (loc >> 3) & 7, x = loc & 7;
-                uint2 raw = buf[s][loc];
-                if (integrate_voxel(raw, gx0 + x, gy0 + y, gz0 + z, P, depth, rgb, sRcp))
-                {
-                    buf[s][loc] = raw;
-                    any = true;
-                }
-            }
-            if (any)
-                sDirty[s] = 1; // benign same-value race
-            fence_proxy_async();
-        }
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(&done[s]);
-    }
-}
-
-// plain LDG/STG variant (one voxel per thread, 8-byte coalesced accesses); kept as the parity cross-check of the
-// TMA pipeline and as a fallback shape for profiling comparisons
-__global__ void __launch_bounds__(512) k_integrate_direct(Voxel *__restrict__ vba, const HashEntry *__restrict__ table,
-                                                           const int *__restrict__ visIds, const int *__restrict__ nVis, IntegrateParams P,
-                                                           const float *__restrict__ depth, const uchar4 *__restrict__ rgb)
-{
-    __shared__ float sRcp[257];
-    const int n = *nVis;
-    const int loc = threadIdx.x;
-    if (loc < 257)
-        sRcp[loc] = c_rcpInt[loc];
-    __syncthreads();
-    const int z = loc >> 6, y = (loc >> 3) & 7, x = loc & 7;
-    for (int i = blockIdx.x; i < n; i += gridDim.x)
-    {
-        HashEntry e = load_entry(table, visIds[i]);
-        if (e.ptr < 0)
-            continue;
-        uint2 *vp = reinterpret_cast<uint2 *>(vba + (size_t)e.ptr * SDF_BLOCK_SIZE3) + loc;
-        uint2 raw = *vp;
-        if (integrate_voxel(raw, (int)e.px * SDF_BLOCK_SIZE + x, (int)e.py * SDF_BLOCK_SIZE + y, (int)e.pz * SDF_BLOCK_SIZE + z, P, depth, rgb, sRcp))
-            *vp = raw;
-    }
-}
+// (Two alternates of this kernel were built, measured equal and removed: one CTA per block with direct loads / stores -- the reference's own
+// shape -- and a warp-specialised pipeline, a producer warp for descriptors / TMA loads / write-back and eight consumer warps handing stages
+// over through mbarriers.  ncu attributes 23 % of this kernel's stall samples to its two CTA barriers per block, but the freed slots were
+// already covered by other warps: the kernel is issue-bound either way.)
 
 // ------------------------------------------------------------------------------------------------------------
 // B6: expected depth range image at 1/8 resolution
@@ -1484,12 +1331,8 @@ void integrate(const Scene &s, const Frame &f, const Camera &cam, int variant, c
     push.n = s.nPush;
     for (int q = 0; q < s.nPush; q++)
         push.p[q] = s.pushVba[q];
-    if (variant == 1 && push.n == 0)
-        k_integrate_direct<<<148 * 4, 512, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
-    else if (variant == 2 && push.n == 0)
-        k_integrate_ws<<<148 * 4, WS_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba);
-    else
-        k_integrate_tma<<<148 * 5, INT_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba, push);
+    (void)variant;
+    k_integrate_tma<<<148 * 5, INT_THREADS, 0, st>>>(s.vba, s.table, ids, nIds, P, f.depth_f, f.rgba, push);
 }
 
 void expected_depth_live(const Scene &s, const Camera &cam, int W, int H, float2 *minmax, cudaStream_t st)

@@ -52,7 +52,7 @@ typedef struct gsb_tsdf_config
     int num_blocks;               /* SDF_LOCAL_BLOCK_NUM, reference 0x40000; 0 = default                      */
     int tracker;                  /* 0 = ground-truth poses (turnOffTracking), 1 = extended, 2 = icp           */
     int device;                   /* CUDA device ordinal                                                       */
-    int integrate_variant;        /* 0 = TMA-pipelined (default), 1 = direct LDG/STG, 2 = warp-specialised TMA pipeline */
+    int integrate_variant;        /* must be 0 (TMA-pipelined kernel); kept so that the struct layout of round 1 callers stays valid */
 } gsb_tsdf_config_t;
 
 void gsb_tsdf_default_config(gsb_tsdf_config_t *cfg);
