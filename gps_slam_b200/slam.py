@@ -138,6 +138,9 @@ class SlamPipeline:
     # ------------------------------------------------------------------------------------------------------------
     def reset(self):
         torch.cuda.synchronize(self.device)
+        if self.world > 1 and parallel.dist.is_available() and parallel.dist.is_initialized():
+            # sharded engines: no rank may clear its map while another one is still storing rows / visibility marks of the last frame into it
+            parallel.dist.barrier()
         self.ev_gs = self.ev_spawn = None
         self.tsdf.resetAll()
         if self.gs:
