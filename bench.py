@@ -327,7 +327,8 @@ def main():
     stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("GSB_MAIN_STREAM_PRIORITY", "-1")))
     # world >= 4: functional split (gps_slam_b200/split.py: rank 0 = the TSDF side, the others = Gaussian shards) unless GSB_SPLIT=0;
     # otherwise every rank runs both sides, Gaussians / voxel hash / ICP sharded
-    split = world >= 4 and track == 0 and mode == "train" and os.environ.get("GSB_SPLIT", "1") != "0"
+    # (BASELINE config 4 names the layout itself -- "Gaussian set + voxel hash sharded across 4xB200" -- so it keeps every rank on both sides)
+    split = world >= 4 and track == 0 and mode == "train" and args.config == 2 and os.environ.get("GSB_SPLIT", "1") != "0"
     if split:
         from gps_slam_b200 import split as split_mod
         pipe = split_mod.SplitSlamPipeline(intr, device=local, stream=stream, rank=rank, world=world,
